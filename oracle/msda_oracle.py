@@ -1,0 +1,269 @@
+"""Python side of the oracle.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Parity status: PINNED against the reference's own ms_deform_attn_core_pytorch through the golden
+vectors in tests/golden/ (made by oracle/gen_golden.py, which imports the reference in the build
+container; checked by tests/test_oracle.py).
+
+Two independent restatements live here:
+
+* ``core_pytorch``  — the reference's CPU path, models/ops/functions/ms_deform_attn_func.py:67-87:
+  per level, a bilinear ``grid_sample`` (zeros padding, align_corners=False) of the level's value
+  map at ``2*loc-1``, weighted by the attention weights and summed over levels x points.  Its
+  backward is torch autograd, exactly how the reference's own test differentiates it.  This is the
+  function bench.py times as the CPU baseline.
+* ``c_forward`` / ``c_backward`` — ctypes calls into oracle/msda_oracle.c, which restates the CUDA
+  kernels' arithmetic (gating, zero padding, gradient formulas; 2-D and the fork's 3-D variant).
+
+Also here: the seeded input generators of SURVEY.md 8(d) and the parity metrics of 8(c).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "_build" / "libmsda_oracle.so"
+_lib = None
+
+# level sets of SURVEY.md section 8
+LEVELS_A = [(45, 80), (23, 40), (12, 20), (6, 10)]       # 360x640  -> S = 4820
+LEVELS_B = [(48, 80), (24, 40), (12, 20), (6, 10)]       # 384x640  -> S = 5100
+LEVELS_C = [(64, 112), (32, 56), (16, 28), (8, 14)]      # 512x896  -> S = 9520
+LEVELS_TEST_PY = [(6, 4), (3, 2)]                        # models/ops/test.py:23
+
+
+# ------------------------------------------------------------------------------------------------
+# restatement 1: the reference's pure-PyTorch path
+# ------------------------------------------------------------------------------------------------
+def core_pytorch(value, spatial_shapes, sampling_locations, attention_weights):
+    """value [N,S,M,D], spatial_shapes [(H,W)...] (list or tensor), sampling_locations
+    [N,Lq,M,L,P,2] in [0,1] (x,y), attention_weights [N,Lq,M,L,P]  ->  [N,Lq,M*D]."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    sizes = [(int(h), int(w)) for h, w in (spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else spatial_shapes)]
+    # heads become batch entries: [N*M, D, S]
+    maps = value.permute(0, 2, 3, 1).reshape(N * M, D, S)
+    # grid_sample wants [-1, 1]; [N*M, Lq, L, P, 2]
+    grid = (2.0 * sampling_locations - 1.0).permute(0, 2, 1, 3, 4, 5).reshape(N * M, Lq, L, P, 2)
+    weights = attention_weights.permute(0, 2, 1, 3, 4).reshape(N * M, 1, Lq, L, P)
+    out = value.new_zeros(N * M, D, Lq)
+    start = 0
+    for lvl, (h, w) in enumerate(sizes):
+        level_map = maps[:, :, start:start + h * w].reshape(N * M, D, h, w)
+        start += h * w
+        sampled = F.grid_sample(level_map, grid[:, :, lvl], mode="bilinear", padding_mode="zeros",
+                                align_corners=False)            # [N*M, D, Lq, P]
+        out = out + (sampled * weights[:, :, :, lvl]).sum(-1)
+    return out.reshape(N, M * D, Lq).transpose(1, 2).contiguous()
+
+
+def core_pytorch_fwd_bwd(value, spatial_shapes, loc, aw, grad_out):
+    """forward + autograd backward through ``core_pytorch``; returns (out, g_value, g_loc, g_aw)."""
+    v = value.detach().clone().requires_grad_(True)
+    l = loc.detach().clone().requires_grad_(True)
+    a = aw.detach().clone().requires_grad_(True)
+    out = core_pytorch(v, spatial_shapes, l, a)
+    gv, gl, ga = torch.autograd.grad(out, (v, l, a), grad_out)
+    return out.detach(), gv, gl, ga
+
+
+# ------------------------------------------------------------------------------------------------
+# restatement 2: C (the CUDA kernels' arithmetic)
+# ------------------------------------------------------------------------------------------------
+def build_c_oracle(force: bool = False) -> Path:
+    src = _HERE / "msda_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        res = subprocess.run(["make", "-C", str(_HERE)] + (["-B"] if force else []), capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return _LIB_PATH
+
+
+def _load_c():
+    global _lib
+    if _lib is None:
+        build_c_oracle()
+        _lib = C.CDLL(str(_LIB_PATH))
+    return _lib
+
+
+def _np(t, dtype):
+    if torch.is_tensor(t):
+        t = t.detach().cpu().numpy()
+    return np.ascontiguousarray(t, dtype=dtype)
+
+
+def _dims(value, loc):
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, LD = loc.shape
+    return N, S, Lq, M, D, L, P, LD
+
+
+def c_forward(value, spatial_shapes, level_start_index, loc, aw, dtype=np.float64, group=0):
+    lib = _load_c()
+    value, loc, aw = _np(value, dtype), _np(loc, dtype), _np(aw, dtype)
+    shapes, lsi = _np(spatial_shapes, np.int64), _np(level_start_index, np.int64)
+    N, S, Lq, M, D, L, P, LD = _dims(value, loc)
+    out = np.empty((N, Lq, M * D), dtype=dtype)
+    fn = lib.msda_oracle_forward_f64 if dtype == np.float64 else lib.msda_oracle_forward_f32
+    fn.restype = None
+    fn(value.ctypes.data_as(C.c_void_p), shapes.ctypes.data_as(C.c_void_p), lsi.ctypes.data_as(C.c_void_p),
+       loc.ctypes.data_as(C.c_void_p), aw.ctypes.data_as(C.c_void_p),
+       C.c_int64(N), C.c_int64(S), C.c_int64(Lq), C.c_int(M), C.c_int(D), C.c_int(L), C.c_int(P),
+       C.c_int(1 if LD == 3 else 0), C.c_int64(group), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def c_backward(value, spatial_shapes, level_start_index, loc, aw, grad_out, dtype=np.float64, group=0):
+    lib = _load_c()
+    value, loc, aw, grad_out = _np(value, dtype), _np(loc, dtype), _np(aw, dtype), _np(grad_out, dtype)
+    shapes, lsi = _np(spatial_shapes, np.int64), _np(level_start_index, np.int64)
+    N, S, Lq, M, D, L, P, LD = _dims(value, loc)
+    gv, gl, ga = np.empty_like(value), np.empty_like(loc), np.empty_like(aw)
+    fn = lib.msda_oracle_backward_f64 if dtype == np.float64 else lib.msda_oracle_backward_f32
+    fn.restype = None
+    fn(value.ctypes.data_as(C.c_void_p), shapes.ctypes.data_as(C.c_void_p), lsi.ctypes.data_as(C.c_void_p),
+       loc.ctypes.data_as(C.c_void_p), aw.ctypes.data_as(C.c_void_p), grad_out.ctypes.data_as(C.c_void_p),
+       C.c_int64(N), C.c_int64(S), C.c_int64(Lq), C.c_int(M), C.c_int(D), C.c_int(L), C.c_int(P),
+       C.c_int(1 if LD == 3 else 0), C.c_int64(group),
+       gv.ctypes.data_as(C.c_void_p), gl.ctypes.data_as(C.c_void_p), ga.ctypes.data_as(C.c_void_p))
+    return gv, gl, ga
+
+
+# ------------------------------------------------------------------------------------------------
+# module prologue (models/ops/modules/ms_deform_attn.py:99-109), for the fused-kernel tests
+# ------------------------------------------------------------------------------------------------
+def prologue(offsets, logits, reference_points, spatial_shapes):
+    """offsets [N,Lq,M,L,P,2], logits [N,Lq,M,L*P], reference_points [N,Lq,L,2|4] ->
+    (sampling_locations [N,Lq,M,L,P,2], attention_weights [N,Lq,M,L,P])."""
+    N, Lq, M, L, P, _ = offsets.shape
+    aw = F.softmax(logits, -1).view(N, Lq, M, L, P)
+    shapes = torch.as_tensor(spatial_shapes, dtype=offsets.dtype, device=offsets.device)
+    if reference_points.shape[-1] == 2:
+        normalizer = torch.stack([shapes[:, 1], shapes[:, 0]], -1)
+        loc = reference_points[:, :, None, :, None, :] + offsets / normalizer[None, None, None, :, None, :]
+    else:
+        loc = reference_points[:, :, None, :, None, :2] + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5
+    return loc, aw
+
+
+# ------------------------------------------------------------------------------------------------
+# seeded synthetic inputs
+# ------------------------------------------------------------------------------------------------
+def level_tensors(levels, device="cpu"):
+    shapes = torch.as_tensor(levels, dtype=torch.long, device=device)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    return shapes, lsi
+
+
+def reference_points_grid(levels, dtype=torch.float32):
+    """Pixel centres of every level, normalised — get_reference_points,
+    models/tce_deformable_transformer.py:572-589 with valid_ratios = 1.  -> [S, 2] (x, y)."""
+    pts = []
+    for (h, w) in levels:
+        ys, xs = torch.meshgrid(torch.linspace(0.5, h - 0.5, h, dtype=dtype),
+                                torch.linspace(0.5, w - 0.5, w, dtype=dtype), indexing="ij")
+        pts.append(torch.stack((xs.reshape(-1) / w, ys.reshape(-1) / h), -1))
+    return torch.cat(pts, 0)
+
+
+def make_inputs(kind, N, levels, Lq=None, M=8, D=32, P=4, seed=0, dtype=torch.float32, three_d=False):
+    """kind: 'testpy' (models/ops/test.py:33-36 — uniform locations, worst-case locality),
+    'model' (encoder-like: reference point = the query's own pixel centre, offsets = the module's
+    init pattern k*dir_m/(W_l,H_l) + N(0, 0.5 px) jitter, softmax weights; primary for roofline),
+    'stress' (U[-0.1,1.1) locations incl. exact-integer and all-outside points).
+    Returns dict(value, shapes, lsi, loc, aw, grad_out) on CPU."""
+    g = torch.Generator().manual_seed(seed)
+    L = len(levels)
+    S = sum(h * w for h, w in levels)
+    shapes, lsi = level_tensors(levels)
+    LD = 3 if three_d else 2
+    if kind == "model":
+        if Lq is None:
+            Lq = S
+        value = torch.randn(N, S, M, D, generator=g)
+        ref = reference_points_grid(levels)                       # [S, 2]
+        if Lq != S:
+            idx = torch.randint(0, S, (Lq,), generator=g)
+            ref = ref[idx]
+        thetas = torch.arange(M, dtype=torch.float32) * (2.0 * np.pi / M)
+        dirs = torch.stack([thetas.cos(), thetas.sin()], -1)
+        dirs = dirs / dirs.abs().max(-1, keepdim=True)[0]         # [M, 2]  (ms_deform_attn.py:63-68)
+        k = torch.arange(1, P + 1, dtype=torch.float32)           # point p -> (p+1) px
+        offs = dirs[:, None, None, :] * k[None, None, :, None]    # [M,1,P,2]
+        offs = offs.expand(M, L, P, 2) + 0.5 * torch.randn(N, Lq, M, L, P, 2, generator=g)
+        wh = torch.tensor([[w, h] for h, w in levels], dtype=torch.float32)   # [L,2] (W,H)
+        loc = ref[None, :, None, None, None, :] + offs / wh[None, None, None, :, None, :]
+        aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    elif kind == "testpy":
+        if Lq is None:
+            Lq = S
+        value = torch.rand(N, S, M, D, generator=g) * 0.01
+        loc = torch.rand(N, Lq, M, L, P, 2, generator=g)
+        aw = torch.rand(N, Lq, M, L, P, generator=g) + 1e-5
+        aw = aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    elif kind == "stress":
+        if Lq is None:
+            Lq = 64
+        value = torch.randn(N, S, M, D, generator=g)
+        loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.2 - 0.1
+        wh = torch.tensor([[w, h] for h, w in levels], dtype=torch.float32)
+        flat = loc.view(N, Lq, M, L, P, 2)
+        # a slice of exact pixel-centre / pixel-edge coordinates and of far-outside points
+        flat[:, 0::7, :, :, 0, :] = (torch.floor(flat[:, 0::7, :, :, 0, :] * wh[None, None, None]) + 0.5) / wh[None, None, None]
+        flat[:, 1::7, :, :, 1 % P, :] = torch.floor(flat[:, 1::7, :, :, 1 % P, :] * wh[None, None, None]) / wh[None, None, None]
+        flat[:, 2::7, :, :, 2 % P, :] = 3.0
+        flat[:, 3::7, :, :, 3 % P, :] = -2.0
+        aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    else:
+        raise ValueError(kind)
+    if three_d:
+        f = torch.rand(N, Lq, M, L, P, 1, generator=g) * 1.2 - 0.1
+        loc = torch.cat([loc, f], -1)
+    grad_out = torch.randn(N, Lq, M * D, generator=g)
+    return dict(value=value.to(dtype).contiguous(), shapes=shapes, lsi=lsi, loc=loc.to(dtype).contiguous(),
+                aw=aw.to(dtype).contiguous(), grad_out=grad_out.to(dtype).contiguous())
+
+
+# ------------------------------------------------------------------------------------------------
+# parity metrics
+# ------------------------------------------------------------------------------------------------
+def max_rel(a, ref):
+    """max |a-ref| / max|ref| — error relative to the tensor's scale (elementwise relative error is
+    meaningless where outputs cancel to ~0)."""
+    a, ref = torch.as_tensor(a).double(), torch.as_tensor(ref).double()
+    scale = ref.abs().max().clamp_min(1e-300)
+    return float(((a - ref).abs().max() / scale))
+
+
+def rel_l2(a, ref):
+    a, ref = torch.as_tensor(a).double(), torch.as_tensor(ref).double()
+    return float((a - ref).norm() / ref.norm().clamp_min(1e-300))
+
+
+def boundary_mask(loc, levels, eps_px=1e-4):
+    """True where a sampling point lies within eps_px of a bilinear cell boundary in x or y (or of
+    the -1 / H gating edges): grad_sampling_loc is discontinuous there, so fp32 and fp64 can pick
+    different cells (SURVEY.md 8c caveat).  loc [N,Lq,M,L,P,2|3] -> bool [N,Lq,M,L,P]."""
+    loc = torch.as_tensor(loc).double()
+    wh = torch.tensor([[w, h] for h, w in levels], dtype=torch.float64)
+    px = loc[..., :2] * wh[None, None, None, :, None, :] - 0.5
+    frac = px - torch.floor(px)
+    near = (frac < eps_px) | (frac > 1 - eps_px)
+    return near.any(-1)
+
+
+def grad_loc_errors(g, ref, loc, levels, eps_px=1e-4):
+    """(max_rel over non-boundary points, rel_l2 over all, boundary fraction)."""
+    g, ref = torch.as_tensor(g).double(), torch.as_tensor(ref).double()
+    mask = boundary_mask(loc, levels, eps_px)
+    keep = (~mask)[..., None].expand_as(ref)
+    scale = ref.abs().max().clamp_min(1e-300)
+    err = ((g - ref).abs() * keep).max() / scale
+    return float(err), rel_l2(g, ref), float(mask.double().mean())

@@ -1,0 +1,291 @@
+// msda_torch.cpp — thin torch binding over the C ABI (include/msda_b200.h).
+//
+// Builds the Python extension module **MultiScaleDeformableAttention_update**, the name the
+// reference imports (models/ops/functions/ms_deform_attn_func.py:18; models/ops/setup.py:53),
+// with the reference's two functions and their exact positional signatures
+// (models/ops/src/vision.cpp:13-16, models/ops/src/ms_deform_attn.h:20-63), so that the
+// reference's functions/, modules/, tce_deformable_transformer.py, tce_rvos.py, engine.py and
+// main.py run on top of it unchanged.  This file contains no kernels and no arithmetic: it
+// checks preconditions the way the reference does (ms_deform_attn_cuda.cu:30-56, :113-143),
+// allocates outputs from the ATen caching allocator, and forwards raw pointers plus the current
+// CUDA stream to libmsda_b200.so.
+//
+// Differences from the reference, all deliberate:
+//   * a CUDAGuard is taken on value's device (the reference relies on torch.cuda.set_device);
+//   * kernel launch failures raise instead of being printf'd (ms_deform_im2col_cuda.cuh:1263-1267);
+//   * no cudaDeviceSynchronize (ms_deform_im2col_cuda.cuh:1260) -> CUDA-graph capturable;
+//   * bf16/f16 are accepted next to float/double; sampling_loc/attn_weight may stay fp32 when
+//     value is 16-bit;
+//   * outputs are at::empty (every element is written) except grad_value.
+
+#include <torch/extension.h>
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include <vector>
+
+#include "../../include/msda_b200.h"
+
+namespace {
+
+int dtype_code(at::ScalarType t, const char *what)
+{
+    switch (t) {
+        case at::kFloat: return MSDA_F32;
+        case at::kBFloat16: return MSDA_BF16;
+        case at::kHalf: return MSDA_F16;
+        case at::kDouble: return MSDA_F64;
+        default: TORCH_CHECK(false, what, " has unsupported dtype ", t);
+    }
+    return -1;
+}
+
+void check_rc(int rc, const char *what)
+{
+    TORCH_CHECK(rc == 0, what, " failed: ", msda_error_string(rc), " (code ", rc, ")");
+}
+
+struct Problem {
+    msda_shape shape;
+    int step;  // min(batch, im2col_step)
+};
+
+Problem make_problem(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                     const at::Tensor &level_start_index, const at::Tensor &sampling_loc,
+                     const at::Tensor &attn_weight, int im2col_step, bool is_3d)
+{
+    // same order and wording as the reference's AT_ASSERTMs
+    TORCH_CHECK(value.is_contiguous(), "value tensor has to be contiguous");
+    TORCH_CHECK(spatial_shapes.is_contiguous(), "spatial_shapes tensor has to be contiguous");
+    TORCH_CHECK(level_start_index.is_contiguous(), "level_start_index tensor has to be contiguous");
+    TORCH_CHECK(sampling_loc.is_contiguous(), "sampling_loc tensor has to be contiguous");
+    TORCH_CHECK(attn_weight.is_contiguous(), "attn_weight tensor has to be contiguous");
+
+    TORCH_CHECK(value.is_cuda(), "value must be a CUDA tensor");
+    TORCH_CHECK(spatial_shapes.is_cuda(), "spatial_shapes must be a CUDA tensor");
+    TORCH_CHECK(level_start_index.is_cuda(), "level_start_index must be a CUDA tensor");
+    TORCH_CHECK(sampling_loc.is_cuda(), "sampling_loc must be a CUDA tensor");
+    TORCH_CHECK(attn_weight.is_cuda(), "attn_weight must be a CUDA tensor");
+
+    TORCH_CHECK(value.dim() == 4, "value must be [N, S, M, D]");
+    TORCH_CHECK(sampling_loc.dim() == 6, "sampling_loc must be [N, Lq, M, L, P, 2|3]");
+    TORCH_CHECK(attn_weight.dim() == 5, "attn_weight must be [N, Lq, M, L, P]");
+    TORCH_CHECK(spatial_shapes.scalar_type() == at::kLong && level_start_index.scalar_type() == at::kLong,
+                "spatial_shapes and level_start_index must be int64");
+    TORCH_CHECK(spatial_shapes.dim() == 2 && spatial_shapes.size(1) == 2, "spatial_shapes must be [L, 2]");
+    TORCH_CHECK(sampling_loc.scalar_type() == attn_weight.scalar_type(),
+                "sampling_loc and attn_weight must share a dtype");
+
+    Problem p;
+    const int64_t batch = value.size(0);
+    p.shape.n_frames = batch;
+    p.shape.spatial_size = value.size(1);
+    p.shape.n_heads = static_cast<int32_t>(value.size(2));
+    p.shape.channels = static_cast<int32_t>(value.size(3));
+    p.shape.n_levels = static_cast<int32_t>(spatial_shapes.size(0));
+    p.shape.n_queries = sampling_loc.size(1);
+    p.shape.n_points = static_cast<int32_t>(sampling_loc.size(4));
+    p.shape.value_dtype = dtype_code(value.scalar_type(), "value");
+    p.shape.loc_dtype = dtype_code(sampling_loc.scalar_type(), "sampling_loc");
+
+    TORCH_CHECK(level_start_index.numel() == p.shape.n_levels, "level_start_index must have one entry per level");
+    TORCH_CHECK(sampling_loc.size(0) == batch && attn_weight.size(0) == batch, "batch size mismatch");
+    TORCH_CHECK(sampling_loc.size(2) == p.shape.n_heads && sampling_loc.size(3) == p.shape.n_levels &&
+                    sampling_loc.size(5) == (is_3d ? 3 : 2),
+                "sampling_loc shape mismatch");
+    TORCH_CHECK(attn_weight.size(1) == p.shape.n_queries && attn_weight.size(2) == p.shape.n_heads &&
+                    attn_weight.size(3) == p.shape.n_levels && attn_weight.size(4) == p.shape.n_points,
+                "attn_weight shape mismatch");
+
+    // ms_deform_attn_cuda.cu:54-56
+    p.step = static_cast<int>(std::min<int64_t>(batch, im2col_step));
+    TORCH_CHECK(msda_check_im2col_step(batch, im2col_step) == 0, "batch(", batch, ") must divide im2col_step(", p.step, ")");
+    return p;
+}
+
+void *stream_of(const at::Tensor &t)
+{
+    return static_cast<void *>(at::cuda::getCurrentCUDAStream(t.get_device()).stream());
+}
+
+}  // namespace
+
+at::Tensor ms_deform_attn_forward(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                  const at::Tensor &level_start_index, const at::Tensor &sampling_loc,
+                                  const at::Tensor &attn_weight, const int im2col_step, const bool is_3d)
+{
+    // models/ops/src/ms_deform_attn.h:29-39 — CUDA only, CPU tensors are an error (no CPU fallback)
+    TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+    const Problem p = make_problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, is_3d);
+    const c10::cuda::CUDAGuard guard(value.device());
+    at::Tensor out = at::empty({p.shape.n_frames, p.shape.n_queries, int64_t(p.shape.n_heads) * p.shape.channels}, value.options());
+    int rc;
+    if (is_3d)
+        rc = msda_forward_3d(&p.shape, p.step, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                             level_start_index.data_ptr<int64_t>(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                             out.data_ptr(), stream_of(value));
+    else
+        rc = msda_forward(&p.shape, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                          level_start_index.data_ptr<int64_t>(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                          out.data_ptr(), stream_of(value));
+    check_rc(rc, "ms_deform_attn_forward");
+    return out;
+}
+
+std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                                const at::Tensor &level_start_index, const at::Tensor &sampling_loc,
+                                                const at::Tensor &attn_weight, const at::Tensor &grad_output,
+                                                const int im2col_step, const bool is_3d)
+{
+    TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+    const Problem p = make_problem(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, is_3d);
+    TORCH_CHECK(grad_output.is_contiguous(), "grad_output tensor has to be contiguous");
+    TORCH_CHECK(grad_output.is_cuda(), "grad_output must be a CUDA tensor");
+    TORCH_CHECK(grad_output.scalar_type() == value.scalar_type(), "grad_output and value must share a dtype");
+    TORCH_CHECK(grad_output.numel() == p.shape.n_frames * p.shape.n_queries * p.shape.n_heads * p.shape.channels,
+                "grad_output shape mismatch");
+    const c10::cuda::CUDAGuard guard(value.device());
+
+    at::Tensor grad_value = at::empty_like(value);             // zero-filled by the library
+    at::Tensor grad_loc = at::empty_like(sampling_loc);        // written once per element
+    at::Tensor grad_aw = at::empty_like(attn_weight);
+    at::Tensor ws;
+    const size_t ws_bytes = msda_backward_workspace_bytes(&p.shape);
+    if (ws_bytes) ws = at::empty({static_cast<int64_t>(ws_bytes / sizeof(float))}, value.options().dtype(at::kFloat));
+    int rc;
+    if (is_3d)
+        rc = msda_backward_3d(&p.shape, p.step, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                              level_start_index.data_ptr<int64_t>(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                              grad_output.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(), grad_aw.data_ptr(),
+                              ws_bytes ? ws.data_ptr() : nullptr, ws_bytes, stream_of(value));
+    else
+        rc = msda_backward(&p.shape, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                           level_start_index.data_ptr<int64_t>(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                           grad_output.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(), grad_aw.data_ptr(),
+                           ws_bytes ? ws.data_ptr() : nullptr, ws_bytes, stream_of(value));
+    check_rc(rc, "ms_deform_attn_backward");
+    return {grad_value, grad_loc, grad_aw};
+}
+
+// ---- additions beyond the reference surface (row f1: fused module prologue) -----------------
+
+namespace {
+
+msda_shape prologue_shape(const at::Tensor &value, const at::Tensor &spatial_shapes, const at::Tensor &level_start_index,
+                          const at::Tensor &offsets, const at::Tensor &logits, const at::Tensor &ref_points)
+{
+    TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+    TORCH_CHECK(value.is_contiguous() && offsets.is_contiguous() && logits.is_contiguous() && ref_points.is_contiguous() &&
+                    spatial_shapes.is_contiguous() && level_start_index.is_contiguous(),
+                "all tensors have to be contiguous");
+    TORCH_CHECK(offsets.is_cuda() && logits.is_cuda() && ref_points.is_cuda() && spatial_shapes.is_cuda() &&
+                    level_start_index.is_cuda(), "all tensors must be CUDA tensors");
+    TORCH_CHECK(value.dim() == 4 && offsets.dim() == 6 && ref_points.dim() == 4, "bad ranks");
+    TORCH_CHECK(spatial_shapes.scalar_type() == at::kLong && level_start_index.scalar_type() == at::kLong,
+                "spatial_shapes and level_start_index must be int64");
+    TORCH_CHECK(offsets.scalar_type() == logits.scalar_type() && offsets.scalar_type() == ref_points.scalar_type(),
+                "offsets, logits and reference_points must share a dtype");
+    msda_shape s;
+    s.n_frames = value.size(0);
+    s.spatial_size = value.size(1);
+    s.n_heads = static_cast<int32_t>(value.size(2));
+    s.channels = static_cast<int32_t>(value.size(3));
+    s.n_levels = static_cast<int32_t>(spatial_shapes.size(0));
+    s.n_queries = offsets.size(1);
+    s.n_points = static_cast<int32_t>(offsets.size(4));
+    s.value_dtype = dtype_code(value.scalar_type(), "value");
+    s.loc_dtype = dtype_code(offsets.scalar_type(), "sampling_offsets");
+    TORCH_CHECK(offsets.size(0) == s.n_frames && offsets.size(2) == s.n_heads && offsets.size(3) == s.n_levels && offsets.size(5) == 2,
+                "sampling_offsets shape mismatch");
+    TORCH_CHECK(logits.numel() == s.n_frames * s.n_queries * s.n_heads * s.n_levels * s.n_points, "logits shape mismatch");
+    TORCH_CHECK(ref_points.size(0) == s.n_frames && ref_points.size(1) == s.n_queries && ref_points.size(2) == s.n_levels &&
+                    (ref_points.size(3) == 2 || ref_points.size(3) == 4),
+                "reference_points must be [N, Lq, L, 2|4]");
+    return s;
+}
+
+}  // namespace
+
+bool ms_deform_attn_prologue_supported(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                       const at::Tensor &offsets, const at::Tensor &ref_points)
+{
+    if (!value.is_cuda() || value.dim() != 4 || offsets.dim() != 6 || ref_points.dim() != 4) return false;
+    msda_shape s;
+    s.n_frames = value.size(0); s.spatial_size = value.size(1);
+    s.n_heads = static_cast<int32_t>(value.size(2)); s.channels = static_cast<int32_t>(value.size(3));
+    s.n_levels = static_cast<int32_t>(spatial_shapes.size(0)); s.n_queries = offsets.size(1);
+    s.n_points = static_cast<int32_t>(offsets.size(4));
+    auto code = [](at::ScalarType t) {
+        return t == at::kFloat ? MSDA_F32 : t == at::kBFloat16 ? MSDA_BF16 : t == at::kHalf ? MSDA_F16 : t == at::kDouble ? MSDA_F64 : -1;
+    };
+    s.value_dtype = code(value.scalar_type());
+    s.loc_dtype = code(offsets.scalar_type());
+    return msda_prologue_supported(&s, static_cast<int>(ref_points.size(3))) != 0;
+}
+
+std::vector<at::Tensor> ms_deform_attn_prologue_forward(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                                        const at::Tensor &level_start_index, const at::Tensor &offsets,
+                                                        const at::Tensor &logits, const at::Tensor &ref_points,
+                                                        const bool materialize)
+{
+    const msda_shape s = prologue_shape(value, spatial_shapes, level_start_index, offsets, logits, ref_points);
+    const c10::cuda::CUDAGuard guard(value.device());
+    at::Tensor out = at::empty({s.n_frames, s.n_queries, int64_t(s.n_heads) * s.channels}, value.options());
+    at::Tensor loc, aw;
+    if (materialize) {
+        loc = at::empty_like(offsets);
+        aw = at::empty({s.n_frames, s.n_queries, s.n_heads, s.n_levels, s.n_points}, offsets.options());
+    }
+    const int rc = msda_prologue_forward(&s, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                                         level_start_index.data_ptr<int64_t>(), offsets.data_ptr(), logits.data_ptr(),
+                                         ref_points.data_ptr(), static_cast<int>(ref_points.size(3)), out.data_ptr(),
+                                         materialize ? loc.data_ptr() : nullptr, materialize ? aw.data_ptr() : nullptr,
+                                         stream_of(value));
+    check_rc(rc, "ms_deform_attn_prologue_forward");
+    if (materialize) return {out, loc, aw};
+    return {out};
+}
+
+std::vector<at::Tensor> ms_deform_attn_prologue_backward(const at::Tensor &value, const at::Tensor &spatial_shapes,
+                                                         const at::Tensor &level_start_index, const at::Tensor &offsets,
+                                                         const at::Tensor &logits, const at::Tensor &ref_points,
+                                                         const at::Tensor &grad_output, const bool need_ref_grad)
+{
+    const msda_shape s = prologue_shape(value, spatial_shapes, level_start_index, offsets, logits, ref_points);
+    TORCH_CHECK(grad_output.is_cuda() && grad_output.is_contiguous() && grad_output.scalar_type() == value.scalar_type(),
+                "grad_output must be a contiguous CUDA tensor of value's dtype");
+    const c10::cuda::CUDAGuard guard(value.device());
+    at::Tensor grad_value = at::empty_like(value);
+    at::Tensor grad_off = at::empty_like(offsets);
+    at::Tensor grad_logit = at::empty_like(logits);
+    at::Tensor grad_ref;
+    if (need_ref_grad) grad_ref = at::empty(ref_points.sizes(), ref_points.options().dtype(at::kFloat));
+    at::Tensor ws;
+    const size_t ws_bytes = msda_backward_workspace_bytes(&s);
+    if (ws_bytes) ws = at::empty({static_cast<int64_t>(ws_bytes / sizeof(float))}, value.options().dtype(at::kFloat));
+    const int rc = msda_prologue_backward(&s, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                                          level_start_index.data_ptr<int64_t>(), offsets.data_ptr(), logits.data_ptr(),
+                                          ref_points.data_ptr(), static_cast<int>(ref_points.size(3)), grad_output.data_ptr(),
+                                          grad_value.data_ptr(), grad_off.data_ptr(), grad_logit.data_ptr(),
+                                          need_ref_grad ? grad_ref.data_ptr<float>() : nullptr,
+                                          ws_bytes ? ws.data_ptr() : nullptr, ws_bytes, stream_of(value));
+    check_rc(rc, "ms_deform_attn_prologue_backward");
+    if (need_ref_grad) return {grad_value, grad_off, grad_logit, grad_ref.to(ref_points.scalar_type())};
+    return {grad_value, grad_off, grad_logit};
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
+{
+    m.doc() = "B200-native (sm_100a) multi-scale deformable attention; drop-in for TCE-RVOS models/ops";
+    // the reference surface (vision.cpp:13-16)
+    m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
+    m.def("ms_deform_attn_backward", &ms_deform_attn_backward, "ms_deform_attn_backward");
+    // additions
+    m.def("ms_deform_attn_prologue_supported", &ms_deform_attn_prologue_supported);
+    m.def("ms_deform_attn_prologue_forward", &ms_deform_attn_prologue_forward);
+    m.def("ms_deform_attn_prologue_backward", &ms_deform_attn_prologue_backward);
+    m.def("launch_count", []() { return msda_launch_count(); });
+    m.def("abi_version", []() { return msda_abi_version(); });
+    m.attr("__b200_native__") = true;
+}
