@@ -6,9 +6,13 @@ from __future__ import annotations
 import importlib
 import sys
 import sysconfig
-from pathlib import Path
+from pathlib import Path  # noqa: E402
 
-NATIVE_DIR = Path(__file__).resolve().parent / "_native"
+import os
+
+# MSDA_NATIVE_DIR: developer override used by tuning sweeps to load an alternative BUILD of the same
+# sources (tools/variants.py); it never points at a different implementation.
+NATIVE_DIR = Path(os.environ.get("MSDA_NATIVE_DIR") or (Path(__file__).resolve().parent / "_native"))
 MODULE_NAME = "MultiScaleDeformableAttention_update"   # models/ops/setup.py:53
 CAPI_NAME = "libmsda_b200.so"
 

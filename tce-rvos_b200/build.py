@@ -118,6 +118,21 @@ def build_torch_binding(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> Path:
+    """Tuning aid: the same sources compiled with extra -D flags into _native_variants/<name>/
+    (the torch binding is copied next to it; its rpath is $ORIGIN)."""
+    build_all(False, verbose)
+    vdir = PKG_DIR / "_native_variants" / name
+    vdir.mkdir(parents=True, exist_ok=True)
+    out = vdir / "libmsda_b200.so"
+    srcs = [CSRC / s for s in CAPI_SOURCES]
+    cmd = [_nvcc(), *ARCH_FLAGS, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-Xcompiler", "-fPIC",
+           "-o", out, *srcs]
+    _run(cmd, verbose)
+    shutil.copy2(module_path(), vdir / module_path().name)
+    return vdir
+
+
 def build_all(force: bool = False, verbose: bool = False):
     return build_capi(force, verbose), build_torch_binding(force, verbose)
 

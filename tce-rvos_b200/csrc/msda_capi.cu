@@ -108,7 +108,7 @@ int launch_fwd_fast(const Dims &d, const void *value, const int64_t *shapes, con
     const int64_t items = d.N * d.Lq * (d.M / HPW);
     if (items == 0) return MSDA_OK;
     constexpr int threads = 256;
-    auto kern = (d.M == 8) ? msda::fwd_fast_kernel<VT, LT, PRO, 8> : msda::fwd_fast_kernel<VT, LT, PRO, 0>;
+    auto kern = (d.M == 8 && d.P == 4) ? msda::fwd_fast_kernel<VT, LT, PRO, true> : msda::fwd_fast_kernel<VT, LT, PRO, false>;
     kern<<<grid_for_warps(items, threads), threads, 0, st>>>(
         static_cast<const VT *>(value), shapes, lsi, static_cast<const LT *>(loc),
         static_cast<const LT *>(aw), static_cast<VT *>(out), items, d.Lq, d.S, d.M, ilog2_exact(d.P), pro);
@@ -197,7 +197,7 @@ int launch_bwd_fast(const Dims &d, const void *value, const int64_t *shapes, con
     const int64_t items = d.N * d.Lq * (d.M / HPW);
     if (items == 0) return MSDA_OK;
     constexpr int threads = 256;
-    auto kern = (d.M == 8) ? msda::bwd_fast_kernel<VT, LT, GT, PRO, 8> : msda::bwd_fast_kernel<VT, LT, GT, PRO, 0>;
+    auto kern = (d.M == 8 && d.P == 4) ? msda::bwd_fast_kernel<VT, LT, GT, PRO, true> : msda::bwd_fast_kernel<VT, LT, GT, PRO, false>;
     kern<<<grid_for_warps(items, threads), threads, 0, st>>>(
         static_cast<const VT *>(value), shapes, lsi, static_cast<const LT *>(loc),
         static_cast<const LT *>(aw), static_cast<const VT *>(go), gv, static_cast<LT *>(gl),

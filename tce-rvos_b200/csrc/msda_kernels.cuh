@@ -128,6 +128,27 @@ template <> struct FastCfg<__nv_bfloat16> {
     static constexpr int LOG_LPH = 2;
 };
 
+// Occupancy targets (CTAs of 256 threads per SM) per kernel family; overridable at build time
+// for tuning sweeps (tools/variants.py).
+#ifndef MSDA_FWD_MIN_BLOCKS_F32
+#define MSDA_FWD_MIN_BLOCKS_F32 4
+#endif
+#ifndef MSDA_FWD_MIN_BLOCKS_BF16
+#define MSDA_FWD_MIN_BLOCKS_BF16 3
+#endif
+#ifndef MSDA_BWD_MIN_BLOCKS_F32
+#define MSDA_BWD_MIN_BLOCKS_F32 3
+#endif
+#ifndef MSDA_BWD_MIN_BLOCKS_BF16
+#define MSDA_BWD_MIN_BLOCKS_BF16 2
+#endif
+#ifndef MSDA_FWD_BATCH
+#define MSDA_FWD_BATCH 2
+#endif
+#ifndef MSDA_EXP
+#define MSDA_EXP 0     // timing experiments only (tools/variants.py); 0 = product
+#endif
+
 constexpr int kFastD = 32;
 constexpr int kFastLP = 16;
 
@@ -140,9 +161,14 @@ template <> struct VecIO<float> {
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
     static __device__ __forceinline__ void zero(float (&v)[4]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
-    static __device__ __forceinline__ void store(float *p, const float (&v)[4])
+    static __device__ __forceinline__ void load_stream(const float *p, float (&v)[4])
     {
-        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        const float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store_stream(float *p, const float (&v)[4])
+    {
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
     }
 };
 template <> struct VecIO<__nv_bfloat16> {
@@ -161,12 +187,22 @@ template <> struct VecIO<__nv_bfloat16> {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
     }
-    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[8])
+    static __device__ __forceinline__ void load_stream(const __nv_bfloat16 *p, float (&v)[8])
+    {
+        const uint4 t = __ldcs(reinterpret_cast<const uint4 *>(p));
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i]     = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store_stream(__nv_bfloat16 *p, const float (&v)[8])
     {
         uint4 t;
         t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
         t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4 *>(p) = t;
+        __stcs(reinterpret_cast<uint4 *>(p), t);
     }
 };
 
@@ -175,50 +211,50 @@ template <typename LT, int PPL> struct PointIO;
 template <> struct PointIO<float, 2> {
     static __device__ __forceinline__ void load_loc(const float *p, float (&xy)[4])
     {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        const float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
         xy[0] = t.x; xy[1] = t.y; xy[2] = t.z; xy[3] = t.w;
     }
     static __device__ __forceinline__ void load_aw(const float *p, float (&a)[2])
     {
-        const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+        const float2 t = __ldcs(reinterpret_cast<const float2 *>(p));
         a[0] = t.x; a[1] = t.y;
     }
     static __device__ __forceinline__ void store_loc(float *p, const float (&xy)[4])
     {
-        *reinterpret_cast<float4 *>(p) = make_float4(xy[0], xy[1], xy[2], xy[3]);
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(xy[0], xy[1], xy[2], xy[3]));
     }
     static __device__ __forceinline__ void store_aw(float *p, const float (&a)[2])
     {
-        *reinterpret_cast<float2 *>(p) = make_float2(a[0], a[1]);
+        __stcs(reinterpret_cast<float2 *>(p), make_float2(a[0], a[1]));
     }
 };
 template <> struct PointIO<float, 4> {
     static __device__ __forceinline__ void load_loc(const float *p, float (&xy)[8])
     {
-        const float4 t0 = __ldg(reinterpret_cast<const float4 *>(p));
-        const float4 t1 = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        const float4 t0 = __ldcs(reinterpret_cast<const float4 *>(p));
+        const float4 t1 = __ldcs(reinterpret_cast<const float4 *>(p) + 1);
         xy[0] = t0.x; xy[1] = t0.y; xy[2] = t0.z; xy[3] = t0.w;
         xy[4] = t1.x; xy[5] = t1.y; xy[6] = t1.z; xy[7] = t1.w;
     }
     static __device__ __forceinline__ void load_aw(const float *p, float (&a)[4])
     {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        const float4 t = __ldcs(reinterpret_cast<const float4 *>(p));
         a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
     }
     static __device__ __forceinline__ void store_loc(float *p, const float (&xy)[8])
     {
-        reinterpret_cast<float4 *>(p)[0] = make_float4(xy[0], xy[1], xy[2], xy[3]);
-        reinterpret_cast<float4 *>(p)[1] = make_float4(xy[4], xy[5], xy[6], xy[7]);
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(xy[0], xy[1], xy[2], xy[3]));
+        __stcs(reinterpret_cast<float4 *>(p) + 1, make_float4(xy[4], xy[5], xy[6], xy[7]));
     }
     static __device__ __forceinline__ void store_aw(float *p, const float (&a)[4])
     {
-        *reinterpret_cast<float4 *>(p) = make_float4(a[0], a[1], a[2], a[3]);
+        __stcs(reinterpret_cast<float4 *>(p), make_float4(a[0], a[1], a[2], a[3]));
     }
 };
 template <> struct PointIO<__nv_bfloat16, 4> {
     static __device__ __forceinline__ void load_loc(const __nv_bfloat16 *p, float (&xy)[8])
     {
-        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+        const uint4 t = __ldcs(reinterpret_cast<const uint4 *>(p));
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -228,7 +264,7 @@ template <> struct PointIO<__nv_bfloat16, 4> {
     }
     static __device__ __forceinline__ void load_aw(const __nv_bfloat16 *p, float (&a)[4])
     {
-        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+        const uint2 t = __ldcs(reinterpret_cast<const uint2 *>(p));
         a[0] = __uint_as_float(t.x << 16); a[1] = __uint_as_float(t.x & 0xffff0000u);
         a[2] = __uint_as_float(t.y << 16); a[3] = __uint_as_float(t.y & 0xffff0000u);
     }
@@ -237,23 +273,24 @@ template <> struct PointIO<__nv_bfloat16, 4> {
         uint4 t;
         t.x = pack_bf16x2(xy[0], xy[1]); t.y = pack_bf16x2(xy[2], xy[3]);
         t.z = pack_bf16x2(xy[4], xy[5]); t.w = pack_bf16x2(xy[6], xy[7]);
-        *reinterpret_cast<uint4 *>(p) = t;
+        __stcs(reinterpret_cast<uint4 *>(p), t);
     }
     static __device__ __forceinline__ void store_aw(__nv_bfloat16 *p, const float (&a)[4])
     {
         uint2 t;
         t.x = pack_bf16x2(a[0], a[1]); t.y = pack_bf16x2(a[2], a[3]);
-        *reinterpret_cast<uint2 *>(p) = t;
+        __stcs(reinterpret_cast<uint2 *>(p), t);
     }
 };
 
-// What one lane knows about a point it owns.
+// What one lane knows about a point it owns.  The first four members are what the other lanes
+// of the head need (4 shuffles per point); the rest stays with the owner.
 struct OwnedPoint {
-    float wa[4];   // bilinear corner weights x attention weight
-    int base;      // pixel index (within the frame) of corner (h_low, w_low); may be negative
-    int rowmask;   // (W << 4) | corner mask
-    // backward only
-    float lh, lw, a;
+    float ta, tb;  // (1-lh)*attn, lh*attn  -> corner weights are ta*hw, ta*lw, tb*hw, tb*lw
+    float lw;
+    int packed;    // (base << 4) | mask; base = pixel index in the frame of corner (h_low, w_low),
+                   // possibly negative (arithmetic shift restores it); mask = corners that are read
+    float lh, a;   // owner only (backward)
     int H, W;
 };
 
@@ -270,17 +307,34 @@ __device__ __forceinline__ OwnedPoint own_point(float x, float y, float a, int H
 {
     OwnedPoint o;
     const PointGeom<float> g = resolve_point<float>(x, y, H, W);
-    const float hh = 1.f - g.lh, hw = 1.f - g.lw;
-    o.wa[0] = hh * hw * a;
-    o.wa[1] = hh * g.lw * a;
-    o.wa[2] = g.lh * hw * a;
-    o.wa[3] = g.lh * g.lw * a;
-    o.base = start + g.h_low * W + g.w_low;
-    o.rowmask = (W << 4) | g.mask;
-    o.lh = g.lh; o.lw = g.lw; o.a = a; o.H = H; o.W = W;
+    o.ta = (1.f - g.lh) * a;
+    o.tb = g.lh * a;
+    o.lw = g.lw;
+    o.packed = ((start + g.h_low * W + g.w_low) << 4) | g.mask;
+    o.lh = g.lh; o.a = a; o.H = H; o.W = W;
     return o;
 }
 
+// A point as seen by every lane of the head after the broadcast.
+struct PointView {
+    float w0, w1, w2, w3;   // corner weights x attention weight
+    int base, mask;
+};
+
+template <int LPH>
+__device__ __forceinline__ PointView view_point(const OwnedPoint &o, int src)
+{
+    const float ta = __shfl_sync(kFull, o.ta, src, LPH);
+    const float tb = __shfl_sync(kFull, o.tb, src, LPH);
+    const float lw = __shfl_sync(kFull, o.lw, src, LPH);
+    const int packed = __shfl_sync(kFull, o.packed, src, LPH);
+    const float hw = 1.f - lw;
+    PointView v;
+    v.w0 = ta * hw; v.w1 = ta * lw; v.w2 = tb * hw; v.w3 = tb * lw;
+    v.base = packed >> 4;
+    v.mask = packed & 15;
+    return v;
+}
 
 // --------------------------------------------------------------------------------------------
 // Fused module prologue (models/ops/modules/ms_deform_attn.py:99-109).  In PROLOGUE mode the
@@ -363,9 +417,11 @@ __device__ __forceinline__ void prologue_points(float (&xy)[2 * PPL], float (&a)
 // --------------------------------------------------------------------------------------------
 // FAST forward.  One warp = HPW heads of one (frame, query).
 //   item = nq * (M / HPW) + head_group
+// TCE = true fixes M = 8 heads, L = 4 levels, P = 4 points at compile time (TCE-RVOS / the
+// Deformable-DETR default): pixel and row strides become immediates / 4 per-level registers.
 // --------------------------------------------------------------------------------------------
-template <typename VT, typename LT, bool PROLOGUE, int MC>
-__global__ void __launch_bounds__(256)
+template <typename VT, typename LT, bool PROLOGUE, bool TCE>
+__global__ void __launch_bounds__(256, (sizeof(VT) == 4 ? MSDA_FWD_MIN_BLOCKS_F32 : MSDA_FWD_MIN_BLOCKS_BF16))
 fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
                 const LT *__restrict__ aw, VT *__restrict__ out,
@@ -378,7 +434,7 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (item >= n_items) return;   // warp-uniform
 
-    if (MC) M = MC;
+    if (TCE) { M = 8; log2P = 2; }
     const int groups = M / HPW;
     const int64_t nq = item / groups;
     const int hg = static_cast<int>(item - nq * groups);
@@ -386,7 +442,7 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     const int g = lane / LPH, j = lane % LPH;
     const int m = hg * HPW + g;
 
-    // ---- own PPL points: coalesced 16-byte loads, resolved once ----
+    // ---- own PPL points: coalesced 16-byte streaming loads, resolved once ----
     const int64_t qh0 = nq * M + hg * HPW;                 // first (query, head) of this warp
     float xy[2 * PPL], a[PPL];
     PointIO<LT, PPL>::load_loc(loc + qh0 * (kFastLP * 2) + lane * (2 * PPL), xy);
@@ -411,102 +467,145 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     for (int pp = 0; pp < PPL; ++pp)
         own[pp] = own_point(xy[2 * pp], xy[2 * pp + 1], a[pp], Hs[pp], Ws[pp], starts[pp]);
 
-    // MC != 0: the head count is a compile-time constant, so the +1-pixel corner offsets
-    // become immediates of the load instruction.  All offsets inside a frame are 32-bit bytes.
-    const int pix = (MC ? MC : M) * kFastD;                // elements between neighbouring pixels
+    // All offsets inside a frame are 32-bit byte offsets.
+    const int pix = M * kFastD;                            // elements between neighbouring pixels
     const int pixb = pix * static_cast<int>(sizeof(VT));   // bytes
     const char *vlane = reinterpret_cast<const char *>(value + n * S * pix + m * kFastD + j * CPL);
+    int rowb[4];                                           // bytes between rows, per level (TCE only)
+    if (TCE) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) rowb[l] = static_cast<int>(__ldg(shapes + 2 * l + 1)) * pixb;
+    }
 
     float acc[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
 
+    // Points are processed in batches of NB: all 4*NB corner loads of a batch are issued before
+    // the first FMA consumes one, so a warp waits on memory 16/NB times instead of 16 times.
+    constexpr int NB = MSDA_FWD_BATCH;
 #pragma unroll
-    for (int p = 0; p < kFastLP; ++p) {
-        const int src = p / PPL, pp = p % PPL;
-        const float w0 = __shfl_sync(kFull, own[pp].wa[0], src, LPH);
-        const float w1 = __shfl_sync(kFull, own[pp].wa[1], src, LPH);
-        const float w2 = __shfl_sync(kFull, own[pp].wa[2], src, LPH);
-        const float w3 = __shfl_sync(kFull, own[pp].wa[3], src, LPH);
-        const int base = __shfl_sync(kFull, own[pp].base, src, LPH);
-        const int rowmask = __shfl_sync(kFull, own[pp].rowmask, src, LPH);
-
-        const char *r0 = vlane + static_cast<int64_t>(base) * pixb;
-        const char *r1 = r0 + static_cast<int64_t>(rowmask >> 4) * pixb;
-        float v0[CPL], v1[CPL], v2[CPL], v3[CPL];
-        VecIO<VT>::zero(v0); VecIO<VT>::zero(v1); VecIO<VT>::zero(v2); VecIO<VT>::zero(v3);
-        if (rowmask & 1) VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v0);
-        if (rowmask & 2) VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v1);
-        if (rowmask & 4) VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v2);
-        if (rowmask & 8) VecIO<VT>::load(reinterpret_cast<const VT *>(r1 + pixb), v3);
+    for (int p0 = 0; p0 < kFastLP; p0 += NB) {
+        PointView pv[NB];
+        float v[NB][4][CPL];
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            acc[c] = fmaf(w0, v0[c], acc[c]);
-            acc[c] = fmaf(w1, v1[c], acc[c]);
-            acc[c] = fmaf(w2, v2[c], acc[c]);
-            acc[c] = fmaf(w3, v3[c], acc[c]);
+        for (int b = 0; b < NB; ++b) {
+            const int p = p0 + b, src = p / PPL, pp = p % PPL;
+#if MSDA_EXP == 4
+            pv[b].w0 = own[pp].ta; pv[b].w1 = own[pp].tb; pv[b].w2 = own[pp].lw; pv[b].w3 = own[pp].lw;
+            pv[b].base = own[pp].packed >> 4; pv[b].mask = own[pp].packed & 15;
+#else
+            pv[b] = view_point<LPH>(own[pp], src);
+#endif
+#if MSDA_EXP == 5
+            pv[b].base &= 63;
+#endif
+            const int rb = TCE ? rowb[p >> 2] : __shfl_sync(kFull, own[pp].W, src, LPH) * pixb;
+            const char *r0 = vlane + static_cast<int64_t>(pv[b].base) * pixb;
+            const char *r1 = r0 + rb;
+#if MSDA_EXP == 1
+            VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v[b][0]);
+            VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v[b][1]);
+            VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v[b][2]);
+            VecIO<VT>::load(reinterpret_cast<const VT *>(r1 + pixb), v[b][3]);
+#else
+#pragma unroll
+            for (int k = 0; k < 4; ++k) VecIO<VT>::zero(v[b][k]);
+            if (pv[b].mask & 1) VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v[b][0]);
+            if (pv[b].mask & 2) VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v[b][1]);
+            if (pv[b].mask & 4) VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v[b][2]);
+            if (pv[b].mask & 8) VecIO<VT>::load(reinterpret_cast<const VT *>(r1 + pixb), v[b][3]);
+#endif
         }
-    }
-
-    VecIO<VT>::store(out + (nq * M + m) * kFastD + j * CPL, acc);
-}
-
-// --------------------------------------------------------------------------------------------
-// Transposing butterfly over the LPH lanes of a head.
-// In : every lane holds partial sums d[p][c] for all 16 points p, 4 corners c.
-// Out: lane j holds the complete sums for the points it owns (p = j*PPL + pp) in d[pp][c].
-// Each round exchanges half of the live values with the partner lane and keeps the other half.
-// --------------------------------------------------------------------------------------------
-template <int LPH>
-__device__ __forceinline__ void butterfly_points(float (&d)[kFastLP][4], int j)
-{
-    // live range [0, n) of point slots; after a round with partner bit b the lane keeps the
-    // upper half if its bit is set, else the lower half; results are compacted to [0, n/2).
 #pragma unroll
-    for (int n = kFastLP, bit = LPH >> 1; bit >= 1; n >>= 1, bit >>= 1) {
-        const bool upper = (j & bit) != 0;
-        const int half = n >> 1;
+        for (int b = 0; b < NB; ++b) {
 #pragma unroll
-        for (int p = 0; p < half; ++p) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float lo = d[p][c], hi = d[p + half][c];
-                const float send = upper ? lo : hi;
-                const float keep = upper ? hi : lo;
-                d[p][c] = keep + __shfl_xor_sync(kFull, send, bit, LPH);
+            for (int c = 0; c < CPL; ++c) {
+                acc[c] = fmaf(pv[b].w0, v[b][0][c], acc[c]);
+                acc[c] = fmaf(pv[b].w1, v[b][1][c], acc[c]);
+                acc[c] = fmaf(pv[b].w2, v[b][2][c], acc[c]);
+                acc[c] = fmaf(pv[b].w3, v[b][3][c], acc[c]);
             }
         }
     }
+
+    VecIO<VT>::store_stream(out + (nq * M + m) * kFastD + j * CPL, acc);
 }
 
 // --------------------------------------------------------------------------------------------
-// FAST backward.  GT is the type grad_value is accumulated in: VT itself (fp32 in place, or
-// direct 16-bit vector atomics) or float (fp32 scratch for 16-bit VT).
+// Transposing reduction over the LPH lanes of a head, done as a tree so that only a handful of
+// partial sums is ever live.  Lane jj owns points jj*PPL + pp.  tree<BIT, PBASE> returns, in every
+// lane, the sum over the 2*BIT lanes of its subtree of the 4 corner dot products of the ONE point
+// of that subtree the lane owns.  Each internal node exchanges 4 values with the partner lane
+// (xor BIT) and keeps 4; leaves gather/scatter one point.  Total: (LP - PPL) * 4 exchanges per
+// warp, the same as a full butterfly, but the live set is 4 * log2(LPH) floats instead of 64.
 // --------------------------------------------------------------------------------------------
+template <int V> struct IntC { static constexpr int value = V; };
+
+template <int BIT, int PBASE, int PPL, int LPH, typename Leaf>
+__device__ __forceinline__ void tree_reduce(int j, Leaf &leaf, float (&res)[4])
+{
+    if constexpr (BIT == 0) {
+        leaf(IntC<PBASE>{}, res);
+    } else {
+        float lo[4], hi[4];
+        tree_reduce<BIT / 2, PBASE, PPL, LPH>(j, leaf, lo);
+        tree_reduce<BIT / 2, PBASE + BIT * PPL, PPL, LPH>(j, leaf, hi);
+        const bool upper = (j & BIT) != 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float send = upper ? lo[c] : hi[c];
+            const float keep = upper ? hi[c] : lo[c];
+            res[c] = keep + __shfl_xor_sync(kFull, send, BIT, LPH);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// grad_value scatter: predicated 16-byte vector reductions (no branch around the instruction).
+// GT is the type grad_value is accumulated in: VT itself (fp32 in place, or direct 16-bit vector
+// atomics) or float (fp32 scratch for 16-bit VT).
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4_f32_if(int pred, void *addr, float a, float b, float c, float d)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t"
+                 "@p red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void red_add_v4_bf16x2_if(int pred, void *addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t"
+                 "@p red.relaxed.gpu.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};\n\t}"
+                 :: "l"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(pred) : "memory");
+}
+
 template <typename VT, typename GT> struct GradScatter;
 template <> struct GradScatter<float, float> {
-    static __device__ __forceinline__ void add(float *p, float w, const float (&go)[4])
+    static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[4])
     {
-        red_add_v4_f32(p, w * go[0], w * go[1], w * go[2], w * go[3]);
+        red_add_v4_f32_if(pred, p, w * go[0], w * go[1], w * go[2], w * go[3]);
     }
 };
 template <> struct GradScatter<__nv_bfloat16, float> {
-    static __device__ __forceinline__ void add(float *p, float w, const float (&go)[8])
+    static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[8])
     {
-        red_add_v4_f32(p, w * go[0], w * go[1], w * go[2], w * go[3]);
-        red_add_v4_f32(p + 4, w * go[4], w * go[5], w * go[6], w * go[7]);
+        red_add_v4_f32_if(pred, p, w * go[0], w * go[1], w * go[2], w * go[3]);
+        red_add_v4_f32_if(pred, p + 16, w * go[4], w * go[5], w * go[6], w * go[7]);
     }
 };
 template <> struct GradScatter<__nv_bfloat16, __nv_bfloat16> {
-    static __device__ __forceinline__ void add(__nv_bfloat16 *p, float w, const float (&go)[8])
+    static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[8])
     {
-        red_add_v4_bf16x2(p, pack_bf16x2(w * go[0], w * go[1]), pack_bf16x2(w * go[2], w * go[3]),
-                          pack_bf16x2(w * go[4], w * go[5]), pack_bf16x2(w * go[6], w * go[7]));
+        red_add_v4_bf16x2_if(pred, p, pack_bf16x2(w * go[0], w * go[1]), pack_bf16x2(w * go[2], w * go[3]),
+                             pack_bf16x2(w * go[4], w * go[5]), pack_bf16x2(w * go[6], w * go[7]));
     }
 };
 
-template <typename VT, typename LT, typename GT, bool PROLOGUE, int MC>
-__global__ void __launch_bounds__(256, (sizeof(VT) == 4 ? 2 : 1))
+// --------------------------------------------------------------------------------------------
+// FAST backward.
+// --------------------------------------------------------------------------------------------
+template <typename VT, typename LT, typename GT, bool PROLOGUE, bool TCE>
+__global__ void __launch_bounds__(256, (sizeof(VT) == 4 ? MSDA_BWD_MIN_BLOCKS_F32 : MSDA_BWD_MIN_BLOCKS_BF16))
 bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
                 const LT *__restrict__ aw, const VT *__restrict__ grad_out,
@@ -520,7 +619,7 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (item >= n_items) return;
 
-    if (MC) M = MC;
+    if (TCE) { M = 8; log2P = 2; }
     const int groups = M / HPW;
     const int64_t nq = item / groups;
     const int hg = static_cast<int>(item - nq * groups);
@@ -534,7 +633,7 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     PointIO<LT, PPL>::load_aw(aw + qh0 * kFastLP + lane * PPL, a);
 
     float go[CPL];
-    VecIO<VT>::load(grad_out + (nq * M + m) * kFastD + j * CPL, go);
+    VecIO<VT>::load_stream(grad_out + (nq * M + m) * kFastD + j * CPL, go);
 
     int Hs[PPL], Ws[PPL], starts[PPL], lv[PPL];
 #pragma unroll
@@ -549,36 +648,38 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     for (int pp = 0; pp < PPL; ++pp)
         own[pp] = own_point(xy[2 * pp], xy[2 * pp + 1], a[pp], Hs[pp], Ws[pp], starts[pp]);
 
-    const int pix = (MC ? MC : M) * kFastD;
+    const int pix = M * kFastD;
     const int pixb = pix * static_cast<int>(sizeof(VT));
     const int gpixb = pix * static_cast<int>(sizeof(GT));
     const int64_t lane_off = n * S * pix + m * kFastD + j * CPL;
     const char *vlane = reinterpret_cast<const char *>(value + lane_off);
     char *glane = reinterpret_cast<char *>(grad_value + lane_off);
-
-    float d[kFastLP][4];
-
+    int rowW[4];
+    if (TCE) {
 #pragma unroll
-    for (int p = 0; p < kFastLP; ++p) {
-        const int src = p / PPL, pp = p % PPL;
-        const float w0 = __shfl_sync(kFull, own[pp].wa[0], src, LPH);
-        const float w1 = __shfl_sync(kFull, own[pp].wa[1], src, LPH);
-        const float w2 = __shfl_sync(kFull, own[pp].wa[2], src, LPH);
-        const float w3 = __shfl_sync(kFull, own[pp].wa[3], src, LPH);
-        const int base = __shfl_sync(kFull, own[pp].base, src, LPH);
-        const int rowmask = __shfl_sync(kFull, own[pp].rowmask, src, LPH);
+        for (int l = 0; l < 4; ++l) rowW[l] = static_cast<int>(__ldg(shapes + 2 * l + 1));
+    }
 
-        const int W = rowmask >> 4;
-        const char *r0 = vlane + static_cast<int64_t>(base) * pixb;
+    // one sampling point: broadcast, gather 4 corners, scatter 4 vector reductions, 4 partial dots
+    auto leaf = [&](auto pc, float (&d)[4]) {
+        constexpr int p = decltype(pc)::value;
+        constexpr int src = p / PPL, pp = p % PPL;
+        const PointView pv = view_point<LPH>(own[pp], src);
+        const int W = TCE ? rowW[p >> 2] : __shfl_sync(kFull, own[pp].W, src, LPH);
+        const char *r0 = vlane + static_cast<int64_t>(pv.base) * pixb;
         const char *r1 = r0 + static_cast<int64_t>(W) * pixb;
-        char *g0 = glane + static_cast<int64_t>(base) * gpixb;
+        char *g0 = glane + static_cast<int64_t>(pv.base) * gpixb;
         char *g1 = g0 + static_cast<int64_t>(W) * gpixb;
         float v0[CPL], v1[CPL], v2[CPL], v3[CPL];
         VecIO<VT>::zero(v0); VecIO<VT>::zero(v1); VecIO<VT>::zero(v2); VecIO<VT>::zero(v3);
-        if (rowmask & 1) { VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v0);        GradScatter<VT, GT>::add(reinterpret_cast<GT *>(g0), w0, go); }
-        if (rowmask & 2) { VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v1); GradScatter<VT, GT>::add(reinterpret_cast<GT *>(g0 + gpixb), w1, go); }
-        if (rowmask & 4) { VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v2);        GradScatter<VT, GT>::add(reinterpret_cast<GT *>(g1), w2, go); }
-        if (rowmask & 8) { VecIO<VT>::load(reinterpret_cast<const VT *>(r1 + pixb), v3); GradScatter<VT, GT>::add(reinterpret_cast<GT *>(g1 + gpixb), w3, go); }
+        if (pv.mask & 1) VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v0);
+        if (pv.mask & 2) VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v1);
+        if (pv.mask & 4) VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v2);
+        if (pv.mask & 8) VecIO<VT>::load(reinterpret_cast<const VT *>(r1 + pixb), v3);
+        GradScatter<VT, GT>::add(pv.mask & 1, g0, pv.w0, go);
+        GradScatter<VT, GT>::add(pv.mask & 2, g0 + gpixb, pv.w1, go);
+        GradScatter<VT, GT>::add(pv.mask & 4, g1, pv.w2, go);
+        GradScatter<VT, GT>::add(pv.mask & 8, g1 + gpixb, pv.w3, go);
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
@@ -587,21 +688,25 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
             d2 = fmaf(go[c], v2[c], d2);
             d3 = fmaf(go[c], v3[c], d3);
         }
-        d[p][0] = d0; d[p][1] = d1; d[p][2] = d2; d[p][3] = d3;
-    }
+        d[0] = d0; d[1] = d1; d[2] = d2; d[3] = d3;
+    };
 
-    butterfly_points<LPH>(d, j);
-
-    // lane now holds the full channel dot products of its own PPL points
+    // lane ends up with the full channel dot products of its own PPL points
     float gxy[2 * PPL], ga[PPL];
 #pragma unroll
     for (int pp = 0; pp < PPL; ++pp) {
+        float d[4];
+        if (pp == 0) tree_reduce<LPH / 2, 0, PPL, LPH>(j, leaf, d);
+        if (pp == 1) tree_reduce<LPH / 2, 1, PPL, LPH>(j, leaf, d);
+        if (PPL > 2) {
+            if (pp == 2) tree_reduce<LPH / 2, 2 % PPL, PPL, LPH>(j, leaf, d);
+            if (pp == 3) tree_reduce<LPH / 2, 3 % PPL, PPL, LPH>(j, leaf, d);
+        }
         const OwnedPoint &o = own[pp];
         const float lh = o.lh, lw = o.lw, hh = 1.f - lh, hw = 1.f - lw;
-        const float d0 = d[pp][0], d1 = d[pp][1], d2 = d[pp][2], d3 = d[pp][3];
-        ga[pp] = hh * hw * d0 + hh * lw * d1 + lh * hw * d2 + lh * lw * d3;
-        const float gw = hh * (d1 - d0) + lh * (d3 - d2);
-        const float gh = hw * (d2 - d0) + lw * (d3 - d1);
+        ga[pp] = hh * hw * d[0] + hh * lw * d[1] + lh * hw * d[2] + lh * lw * d[3];
+        const float gw = hh * (d[1] - d[0]) + lh * (d[3] - d[2]);
+        const float gh = hw * (d[2] - d[0]) + lw * (d[3] - d[1]);
         gxy[2 * pp]     = static_cast<float>(o.W) * gw * o.a;
         gxy[2 * pp + 1] = static_cast<float>(o.H) * gh * o.a;
     }

@@ -38,7 +38,11 @@ def gather_frames(local: torch.Tensor, n_frames: int, group=None) -> torch.Tenso
     operator's data path)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    sizes = [frame_range(n_frames, r, world) for r in range(world)]
-    parts = [local.new_empty((b - a,) + tuple(local.shape[1:])) for a, b in sizes]
-    dist.all_gather(parts, local.contiguous(), group=group)
-    return torch.cat(parts, 0)
+    sizes = [b - a for a, b in (frame_range(n_frames, r, world) for r in range(world))]
+    biggest = max(sizes)
+    # all_gather wants equal shapes on every rank: pad the short shards, trim after
+    padded = local.new_zeros((biggest,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], 0)

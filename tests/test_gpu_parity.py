@@ -1,0 +1,421 @@
+"""Parity of the CUDA path with the oracle — the tests proper (run with `-m gpu` on a B200).
+
+Everything here goes through the C ABI: either directly (capi.forward / capi.backward = ctypes on
+libmsda_b200.so) or through the torch binding that forwards to the same entry points.
+
+Tolerances (BASELINE.json north_star): fp32 forward within 1e-5 of an fp64 run of the reference
+algorithm, gradients within 1e-4, bf16 within 1e-2; errors are measured relative to the tensor's
+scale (max |a-b| / max |b|), and grad_sampling_loc excludes points within 1e-4 px (fp32; 2e-2 px
+for bf16 locations) of a bilinear cell boundary, where the gradient is discontinuous.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+FWD_TOL, GRAD_TOL, BF16_TOL = 1e-5, 1e-4, 1e-2
+
+
+def to_dev(g, dtype, keys=("value", "loc", "aw", "grad_out")):
+    t = {k: torch.from_numpy(np.asarray(g[k])).to(DEV, dtype).contiguous() for k in keys}
+    t["shapes"] = torch.from_numpy(np.asarray(g["shapes"])).to(DEV)
+    t["lsi"] = torch.from_numpy(np.asarray(g["lsi"])).to(DEV)
+    return t
+
+
+def dev_inputs(inp, dtype, loc_dtype=None):
+    loc_dtype = loc_dtype or dtype
+    return dict(value=inp["value"].to(DEV, dtype), loc=inp["loc"].to(DEV, loc_dtype), aw=inp["aw"].to(DEV, loc_dtype),
+                grad_out=inp["grad_out"].to(DEV, dtype), shapes=inp["shapes"].to(DEV), lsi=inp["lsi"].to(DEV))
+
+
+def check_grads(O, got, ref, loc, levels, tol, eps_px=1e-4, stress=False):
+    gv, gl, ga = got
+    rv, rl, ra = ref
+    assert O.max_rel(gv.cpu(), rv) < tol, ("grad_value", O.max_rel(gv.cpu(), rv))
+    assert O.max_rel(ga.cpu(), ra) < tol, ("grad_attn", O.max_rel(ga.cpu(), ra))
+    err, l2, frac = O.grad_loc_errors(gl.cpu(), rl, loc, levels, eps_px)
+    assert err < tol, ("grad_loc", err, l2, frac)
+    if not stress:
+        assert l2 < 10 * tol, ("grad_loc rel-L2", l2, frac)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors of the reference (every case, fp64 generic kernels and fp32 fast/generic kernels)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fp64_through_c_abi(capi, oracle, name):
+    g = load_golden(name)
+    t = to_dev(g, torch.float64)
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    assert oracle.max_rel(out.cpu().view(g["out"].shape), g["out"]) < 1e-12
+    got = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    check_grads(oracle, got, (g["grad_value"], g["grad_loc"], g["grad_aw"]), g["loc"], g["shapes"].tolist(),
+                1e-11, eps_px=1e-9, stress=str(g["kind"]) == "stress")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fp32_through_c_abi(capi, oracle, name):
+    g = load_golden(name)
+    t = to_dev(g, torch.float32)
+    # the fp64 truth for fp32-rounded inputs is the golden itself up to input rounding (1e-7)
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(t["value"].cpu().double(), g["shapes"], t["loc"].cpu().double(),
+                                                      t["aw"].cpu().double(), t["grad_out"].cpu().double())
+    assert oracle.max_rel(out.cpu(), ref_out) < FWD_TOL
+    got = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    check_grads(oracle, got, (rv, rl, ra), t["loc"].cpu(), g["shapes"].tolist(), GRAD_TOL,
+                stress=str(g["kind"]) == "stress")
+
+
+def test_fast_kernels_are_selected_for_tce_geometry(capi):
+    lib = capi.load()
+    sh = capi.make_shape(2, 83, 83, 8, 32, 4, 4, capi.MSDA_F32, capi.MSDA_F32)
+    assert lib.msda_kernel_name(C.byref(sh), 0) == b"fwd_fast_d32_f32"
+
+
+# ------------------------------------------------------------------------------------------------
+# torch binding == C ABI, autograd plumbing, reference test.py checks
+# ------------------------------------------------------------------------------------------------
+def test_autograd_function_matches_c_abi(pkg, capi, oracle):
+    inp = oracle.make_inputs("model", 2, [(12, 20), (6, 10), (3, 5), (2, 3)], seed=1)
+    t = dev_inputs(inp, torch.float32)
+    v, l, a = (t[k].clone().requires_grad_(True) for k in ("value", "loc", "aw"))
+    out = pkg.MSDeformAttnFunction.apply(v, t["shapes"], t["lsi"], l, a, 64)
+    out.backward(t["grad_out"])
+    out2 = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    assert torch.equal(out, out2)                       # same kernel, deterministic forward
+    gv, gl, ga = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    assert torch.equal(l.grad, gl) and torch.equal(a.grad, ga)      # written once, no atomics
+    assert oracle.max_rel(v.grad.cpu(), gv.cpu()) < 1e-6            # atomics: order may differ
+
+
+def test_reference_test_py_forward_and_gradcheck(pkg, oracle):
+    """models/ops/test.py: forward double (:31-44), forward float (:47-60), gradcheck in fp64 for
+    D in {30,32,64,71,1025,2048,3096} (:63-78,:85-86)."""
+    levels = oracle.LEVELS_TEST_PY
+    inp = oracle.make_inputs("testpy", 1, levels, Lq=2, M=2, D=2, P=2, seed=3, dtype=torch.float64)
+    t = dev_inputs(inp, torch.float64)
+    ref = oracle.core_pytorch(inp["value"], inp["shapes"], inp["loc"], inp["aw"])
+    out = pkg.MSDeformAttnFunction.apply(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], 2)
+    assert torch.allclose(out.cpu(), ref)
+    out32 = pkg.MSDeformAttnFunction.apply(t["value"].float(), t["shapes"], t["lsi"], t["loc"].float(), t["aw"].float(), 2)
+    assert torch.allclose(out32.cpu().double(), ref, rtol=1e-2, atol=1e-3)
+    for D in (30, 32, 64, 71, 1025, 2048, 3096):
+        inp = oracle.make_inputs("testpy", 1, levels, Lq=2, M=2, D=D, P=2, seed=D, dtype=torch.float64)
+        t = dev_inputs(inp, torch.float64)
+        v, l, a = (t[k].requires_grad_(True) for k in ("value", "loc", "aw"))
+        assert torch.autograd.gradcheck(pkg.MSDeformAttnFunction.apply, (v, t["shapes"], t["lsi"], l, a, 2)), D
+
+
+def test_preconditions_raise_like_the_reference(pkg, oracle):
+    inp = oracle.make_inputs("model", 3, [(4, 4)], Lq=4, M=8, D=32, P=16, seed=0)
+    t = dev_inputs(inp, torch.float32)
+    f = pkg.MSDeformAttnFunction.apply
+    with pytest.raises(RuntimeError, match="contiguous"):
+        f(t["value"].transpose(0, 1).contiguous().transpose(0, 1), t["shapes"], t["lsi"], t["loc"], t["aw"], 64)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        f(t["value"], t["shapes"].cpu(), t["lsi"], t["loc"], t["aw"], 64)
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        f(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], 2)       # 3 % 2 != 0 (.cu:54-56)
+    assert f(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], 3).shape == (3, 4, 256)
+
+
+def test_empty_inputs(pkg, capi, oracle):
+    inp = oracle.make_inputs("model", 2, [(4, 4)], Lq=4, M=8, D=32, P=16, seed=0)
+    t = dev_inputs(inp, torch.float32)
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"][:, :0].contiguous(), t["aw"][:, :0].contiguous())
+    assert out.shape == (2, 0, 256)
+    gv, gl, ga = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"][:, :0].contiguous(),
+                               t["aw"][:, :0].contiguous(), t["grad_out"][:, :0].contiguous())
+    assert float(gv.abs().max()) == 0.0 and gl.numel() == 0 and ga.numel() == 0
+    out0 = capi.forward(t["value"][:0], t["shapes"], t["lsi"], t["loc"][:0], t["aw"][:0])
+    assert out0.shape == (0, 4, 256)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json config 2 at full size: N = 2x5 frames, level-set A, Lq = S, fp32 and bf16
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["model", "testpy"])
+def test_config2_fp32_against_fp64_oracle(capi, oracle, kind):
+    levels = oracle.LEVELS_A
+    inp = oracle.make_inputs(kind, 10, levels, seed=0)
+    t = dev_inputs(inp, torch.float32)
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    got = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(inp["value"].double(), inp["shapes"], inp["loc"].double(),
+                                                      inp["aw"].double(), inp["grad_out"].double())
+    assert oracle.max_rel(out.cpu(), ref_out) < FWD_TOL
+    check_grads(oracle, got, (rv, rl, ra), inp["loc"], levels, GRAD_TOL)
+
+
+@pytest.mark.parametrize("loc_dtype", [torch.float32, torch.bfloat16])
+def test_config2_bf16_against_fp64_oracle(capi, oracle, loc_dtype):
+    levels = oracle.LEVELS_A
+    inp = oracle.make_inputs("model", 10, levels, seed=1)
+    t = dev_inputs(inp, torch.bfloat16, loc_dtype)
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    got = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    # truth: fp64 run of the reference algorithm on the SAME (bf16-rounded) inputs
+    ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(t["value"].cpu().double(), inp["shapes"], t["loc"].cpu().double(),
+                                                      t["aw"].cpu().double(), t["grad_out"].cpu().double())
+    assert oracle.max_rel(out.float().cpu(), ref_out) < BF16_TOL
+    gv, gl, ga = (x.float() for x in got)
+    eps = 1e-4 if loc_dtype == torch.float32 else 2e-2
+    check_grads(oracle, (gv, gl, ga), (rv, rl, ra), t["loc"].float().cpu(), levels, BF16_TOL, eps_px=eps)
+    # direct 16-bit vector atomics (no fp32 scratch): one rounding per contribution -> looser
+    gv2, gl2, ga2 = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"], use_workspace=False)
+    assert oracle.max_rel(gv2.float().cpu(), rv) < 1.5e-1
+    assert torch.equal(gl2, got[1]) and torch.equal(ga2, got[2])
+
+
+def test_decoder_and_ftf_shapes(capi, oracle):
+    """Lq = 5 (decoder) and Lq = 8 (FTF) on a 36-frame clip (BASELINE.json config 3 geometry)."""
+    levels = oracle.LEVELS_A
+    for Lq, seed in ((5, 2), (8, 3)):
+        inp = oracle.make_inputs("model", 36, levels, Lq=Lq, seed=seed)
+        t = dev_inputs(inp, torch.float32)
+        out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+        got = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+        ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(inp["value"].double(), inp["shapes"], inp["loc"].double(),
+                                                          inp["aw"].double(), inp["grad_out"].double())
+        assert oracle.max_rel(out.cpu(), ref_out) < FWD_TOL
+        check_grads(oracle, got, (rv, rl, ra), inp["loc"], levels, GRAD_TOL)
+
+
+def test_stress_locations_fp32(capi, oracle):
+    levels = oracle.LEVELS_B
+    inp = oracle.make_inputs("stress", 5, levels, Lq=512, seed=4)
+    t = dev_inputs(inp, torch.float32)
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    got = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    # the C oracle restates the kernels' own gating, so exact-integer coordinates are comparable
+    ref_out = oracle.c_forward(inp["value"], inp["shapes"], inp["lsi"], inp["loc"], inp["aw"], np.float64)
+    rv, rl, ra = oracle.c_backward(inp["value"], inp["shapes"], inp["lsi"], inp["loc"], inp["aw"], inp["grad_out"], np.float64)
+    assert oracle.max_rel(out.cpu().view(ref_out.shape), ref_out) < FWD_TOL
+    check_grads(oracle, got, (rv, rl, ra), inp["loc"], levels, GRAD_TOL, stress=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at the scaling-sweep size (BASELINE.json config 5: level-set C)
+# ------------------------------------------------------------------------------------------------
+def test_properties_at_sweep_size(capi, oracle):
+    levels = oracle.LEVELS_C
+    N = 64
+    inp = oracle.make_inputs("model", 2, levels, seed=5)
+    S = inp["value"].shape[1]
+    g = torch.Generator(device=DEV).manual_seed(0)
+    loc = inp["loc"].to(DEV).repeat(N // 2, 1, 1, 1, 1, 1).contiguous()
+    aw = inp["aw"].to(DEV).repeat(N // 2, 1, 1, 1, 1).contiguous()
+    shapes, lsi = inp["shapes"].to(DEV), inp["lsi"].to(DEV)
+    v1 = torch.randn(N, S, 8, 32, device=DEV, generator=g)
+    v2 = torch.randn(N, S, 8, 32, device=DEV, generator=g)
+    o1 = capi.forward(v1, shapes, lsi, loc, aw)
+    o2 = capi.forward(v2, shapes, lsi, loc, aw)
+    o12 = capi.forward(v1 + v2, shapes, lsi, loc, aw)
+    # linearity in value
+    assert oracle.max_rel((o1 + o2).cpu(), o12.cpu()) < 1e-5
+    # frame-permutation equivariance, bitwise: frames are independent (the sharding property)
+    perm = torch.randperm(N, device=DEV, generator=g)
+    op = capi.forward(v1[perm].contiguous(), shapes, lsi, loc[perm].contiguous(), aw[perm].contiguous())
+    assert torch.equal(op, o1[perm])
+    # partition of unity: constant value, all points strictly inside -> out == sum(attn) == 1
+    loc_in = loc.clamp(0.07, 0.93)              # >= half a pixel inside even on the 8x14 level
+    ones = torch.ones_like(v1)
+    o = capi.forward(ones, shapes, lsi, loc_in, aw)
+    assert float((o - 1).abs().max()) < 1e-5
+    # checksum of the scatter: sum_S grad_value[n,:,m,c] == sum_q grad_out[n,q,m,c] (weights sum to 1)
+    go = torch.randn(N, S, 256, device=DEV, generator=g)
+    gv, gl, ga = capi.backward(ones, shapes, lsi, loc_in, aw, go)
+    lhs = gv.double().sum(1).view(N, 256)
+    rhs = go.double().sum(1)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-5
+    # constant value field -> no location gradient, attention gradient = sum_c grad_out
+    assert float(gl.abs().max()) < 1e-3 * float(go.abs().max())
+    ga_ref = go.view(N, S, 8, 32).sum(-1)[..., None, None].expand_as(ga)
+    assert oracle.max_rel(ga.cpu(), ga_ref.cpu()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# fused module prologue (row f1) and the MSDeformAttn module
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_prologue(pkg, oracle, ref_dim, dtype):
+    levels = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    N, Lq, M, L, P = 3, 50, 8, 4, 4
+    g = torch.Generator().manual_seed(7)
+    S = sum(h * w for h, w in levels)
+    value = torch.randn(N, S, M, 32, generator=g)
+    offsets = torch.randn(N, Lq, M, L, P, 2, generator=g) * 2.0
+    logits = torch.randn(N, Lq, M, L * P, generator=g)
+    ref = torch.rand(N, Lq, L, ref_dim, generator=g)
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:] * 0.3 + 0.05
+    go = torch.randn(N, Lq, M * 32, generator=g)
+    shapes, lsi = oracle.level_tensors(levels)
+    ldt = torch.float32
+    dv, doff, dlog, dref, dgo = (x.to(DEV, d).contiguous().requires_grad_(r) for x, d, r in
+                                 ((value, dtype, True), (offsets, ldt, True), (logits, ldt, True), (ref, ldt, True), (go, dtype, False)))
+    out, loc, aw = pkg.MSDeformAttnPrologueFunction.apply(dv, shapes.to(DEV), lsi.to(DEV), doff, dlog, dref, True)
+    out.backward(dgo)
+    # fp64 truth on the same (rounded) inputs: torch prologue + reference algorithm + autograd
+    tv, toff, tlog, tref = (x.detach().cpu().double().requires_grad_(True) for x in (dv, doff, dlog, dref))
+    tloc, taw = oracle.prologue(toff, tlog, tref, levels)
+    tout = oracle.core_pytorch(tv, shapes, tloc, taw)
+    tout.backward(dgo.cpu().double())
+    tol_f, tol_g = (FWD_TOL, GRAD_TOL) if dtype == torch.float32 else (BF16_TOL, BF16_TOL)
+    assert oracle.max_rel(loc.cpu(), tloc.detach()) < 1e-6
+    assert oracle.max_rel(aw.cpu(), taw.detach()) < 1e-6
+    assert oracle.max_rel(out.float().cpu(), tout.detach()) < tol_f
+    assert oracle.max_rel(dv.grad.float().cpu(), tv.grad) < tol_g
+    assert oracle.max_rel(dlog.grad.cpu(), tlog.grad) < tol_g
+    assert oracle.max_rel(dref.grad.cpu(), tref.grad) < 10 * tol_g      # sums ~128 cell-sensitive terms
+    err, l2, frac = oracle.grad_loc_errors(doff.grad.cpu(), toff.grad, tloc.detach(), levels)
+    assert err < tol_g, (err, l2, frac)
+    # without materialisation the output is identical
+    out2 = pkg.MSDeformAttnPrologueFunction.apply(dv.detach(), shapes.to(DEV), lsi.to(DEV), doff.detach(), dlog.detach(), dref.detach(), False)
+    assert torch.equal(out2, out.detach())
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_module_forward_backward_against_oracle_composition(pkg, oracle, fused, ref_dim):
+    levels = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in levels)
+    N, Lq = 2, 40
+    torch.manual_seed(0)
+    m = pkg.MSDeformAttn(256, 4, 8, 4)
+    with torch.no_grad():                                    # random (not init) weights so every path matters
+        m.sampling_offsets.weight.normal_(0, 0.02)
+        m.attention_weights.weight.normal_(0, 0.1)
+    m = m.to(DEV)
+    m.fused_prologue = fused
+    query = torch.randn(N, Lq, 256)
+    src = torch.randn(N, S, 256)
+    ref = torch.rand(N, Lq, 4, ref_dim) * (0.4 if ref_dim == 4 else 1.0) + 0.05
+    mask = torch.zeros(N, S, dtype=torch.bool)
+    mask[:, -7:] = True
+    shapes, lsi = oracle.level_tensors(levels)
+    q, s_ = query.to(DEV).requires_grad_(True), src.to(DEV).requires_grad_(True)
+    out, loc, aw = m(q, ref.to(DEV), s_, shapes.to(DEV), lsi.to(DEV), mask.to(DEV))
+    assert out.shape == (N, Lq, 256) and loc.shape == (N, Lq, 8, 4, 4, 2) and aw.shape == (N, Lq, 8, 4, 4)
+    out.sum().backward()
+    # oracle composition in fp64 with the same weights (ms_deform_attn.py:95-115)
+    md = pkg.MSDeformAttn(256, 4, 8, 4).double()
+    md.load_state_dict({k: v.double().cpu() for k, v in m.state_dict().items()})
+    qd, sd = query.double().requires_grad_(True), src.double().requires_grad_(True)
+    val = md.value_proj(sd).masked_fill(mask[..., None], 0.0).view(N, S, 8, 32)
+    off = md.sampling_offsets(qd).view(N, Lq, 8, 4, 4, 2)
+    log = md.attention_weights(qd).view(N, Lq, 8, 16)
+    tloc, taw = oracle.prologue(off, log, ref.double(), levels)
+    tout = md.output_proj(oracle.core_pytorch(val, shapes, tloc, taw))
+    tout.sum().backward()
+    assert oracle.max_rel(out.detach().cpu(), tout.detach()) < 5e-5     # includes fp32 cuBLAS Linear layers
+    assert oracle.max_rel(loc.detach().cpu(), tloc.detach()) < 1e-5
+    assert oracle.max_rel(aw.detach().cpu(), taw.detach()) < 1e-5
+    assert oracle.max_rel(s_.grad.cpu(), sd.grad) < 1e-3
+    assert oracle.rel_l2(q.grad.cpu(), qd.grad) < 1e-3
+    if fused:
+        m.return_sampling = False
+        o2, l2_, a2 = m(q.detach(), ref.to(DEV), s_.detach(), shapes.to(DEV), lsi.to(DEV), mask.to(DEV))
+        assert l2_ is None and a2 is None and torch.equal(o2, out.detach())
+
+
+# ------------------------------------------------------------------------------------------------
+# the fork's 3-D variant (row f4)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol_f,tol_g", [(torch.float64, 1e-12, 1e-11), (torch.float32, FWD_TOL, GRAD_TOL)])
+def test_3d_variant_against_c_oracle(pkg, oracle, dtype, tol_f, tol_g):
+    levels = [(6, 7), (3, 4)]
+    N, step = 4, 2                                            # two groups of two frames (im2col_step chunks)
+    inp = oracle.make_inputs("stress", N, levels, Lq=9, M=4, D=32, P=2, seed=9, dtype=torch.float64, three_d=True)
+    t = dev_inputs(inp, dtype)
+    v, l, a = (t[k].clone().requires_grad_(True) for k in ("value", "loc", "aw"))
+    out = pkg.MSDeformAttnFunction3D.apply(v, t["shapes"], t["lsi"], l, a, step)
+    out.backward(t["grad_out"])
+    src = {k: t[k].cpu().double() for k in ("value", "loc", "aw", "grad_out")}
+    ref_out = oracle.c_forward(src["value"], inp["shapes"], inp["lsi"], src["loc"], src["aw"], np.float64, group=step)
+    rv, rl, ra = oracle.c_backward(src["value"], inp["shapes"], inp["lsi"], src["loc"], src["aw"], src["grad_out"],
+                                   np.float64, group=step)
+    assert oracle.max_rel(out.detach().cpu().view(ref_out.shape), ref_out) < tol_f
+    assert oracle.max_rel(v.grad.cpu(), rv) < tol_g
+    assert oracle.max_rel(a.grad.cpu(), ra) < tol_g
+    eps = 1e-9 if dtype == torch.float64 else 1e-4
+    mask = oracle.boundary_mask(src["loc"], levels, eps)
+    fi = src["loc"][..., 2] * step - 0.5
+    mask |= ((fi - fi.floor()) < eps) | ((fi - fi.floor()) > 1 - eps)
+    keep = (~mask)[..., None].expand_as(l.grad).cpu()
+    scale = float(np.abs(rl).max())
+    assert float(((l.grad.cpu().double() - torch.from_numpy(rl)).abs() * keep).max()) / scale < tol_g
+
+
+# ------------------------------------------------------------------------------------------------
+# host-buffer API, streams, CUDA graphs, multi-GPU frame sharding
+# ------------------------------------------------------------------------------------------------
+def test_host_buffer_api_matches_device_api(capi, oracle):
+    levels = oracle.LEVELS_A
+    inp = oracle.make_inputs("model", 5, levels, Lq=600, seed=6)
+    t = dev_inputs(inp, torch.float32)
+    out_d = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    gv_d, gl_d, ga_d = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    sh = capi.shape_of(inp["value"], inp["loc"], len(levels))
+    ctx = capi.HostContext(0)
+    pin = {k: inp[k].pin_memory() for k in ("value", "loc", "aw", "grad_out")}
+    out = torch.empty(5, 600, 256).pin_memory()
+    gv, gl, ga = (torch.empty_like(inp[k]).pin_memory() for k in ("value", "loc", "aw"))
+    for _ in range(2):                                          # second call reuses the staging
+        ctx.forward_backward(sh, pin["value"], inp["shapes"], inp["lsi"], pin["loc"], pin["aw"], pin["grad_out"],
+                             out, gv, gl, ga)
+    assert torch.equal(out, out_d.cpu()) and torch.equal(gl, gl_d.cpu()) and torch.equal(ga, ga_d.cpu())
+    assert oracle.max_rel(gv, gv_d.cpu()) < 1e-6
+    out2 = np.empty((5, 600, 256), dtype=np.float32)            # pageable numpy buffers work too
+    ctx.forward(sh, inp["value"].numpy(), inp["shapes"].numpy(), inp["lsi"].numpy(), inp["loc"].numpy(),
+                inp["aw"].numpy(), out2)
+    assert np.array_equal(out2, out_d.cpu().numpy())
+    ctx.close()
+
+
+def test_runs_on_current_stream_and_in_cuda_graph(pkg, capi, oracle):
+    inp = oracle.make_inputs("model", 4, [(12, 20), (6, 10), (3, 5), (2, 3)], seed=8)
+    t = dev_inputs(inp, torch.float32)
+    expect = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    egv, egl, ega = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        # warm-up on the side stream, then capture: needs a launch path with no sync and no allocation
+        ext = pkg.load_extension()
+        for _ in range(2):
+            o = ext.ms_deform_attn_forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], 64, False)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            o = ext.ms_deform_attn_forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], 64, False)
+            gv, gl, ga = ext.ms_deform_attn_backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"], 64, False)
+        o.zero_(); gl.zero_(); ga.zero_()
+        graph.replay()
+    side.synchronize()
+    assert torch.equal(o, expect) and torch.equal(gl, egl) and torch.equal(ga, ega)
+    assert oracle.max_rel(gv.cpu(), egv.cpu()) < 1e-6
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_frame_sharding_across_two_gpus(pkg, oracle):
+    import importlib
+    sh = importlib.import_module("tce-rvos_b200.sharding")
+    inp = oracle.make_inputs("model", 5, [(12, 20), (6, 10), (3, 5), (2, 3)], seed=10)
+    t = dev_inputs(inp, torch.float32)
+    whole = pkg.MSDeformAttnFunction.apply(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], 64)
+    parts = []
+    for r in range(2):
+        d = f"cuda:{r}"
+        v, l, a = (x.to(d).contiguous() for x in sh.shard_frames(r, 2, inp["value"], inp["loc"], inp["aw"]))
+        parts.append(pkg.MSDeformAttnFunction.apply(v, inp["shapes"].to(d), inp["lsi"].to(d), l, a, 64).cpu())
+    assert torch.equal(torch.cat(parts, 0), whole.cpu())
