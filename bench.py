@@ -144,8 +144,21 @@ def cpu_step(inp):
     return O.core_pytorch_fwd_bwd(inp["value"], inp["shapes"], inp["loc"], inp["aw"], inp["grad_out"])
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core it is allowed."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return n
+
+
 def time_cpu(frames, warmup, steps, lq=None):
     import torch
+    use_all_host_threads()
     inp = cpu_step_inputs(frames, lq)
     for _ in range(warmup):
         cpu_step(inp)

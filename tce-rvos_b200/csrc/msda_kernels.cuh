@@ -586,11 +586,17 @@ template <> struct GradScatter<float, float> {
         red_add_v4_f32_if(pred, p, w * go[0], w * go[1], w * go[2], w * go[3]);
     }
 };
+// fp32 scratch for 16-bit values.  A lane holds 8 consecutive channels; written naively its two
+// 16-byte reductions would each cover HALF of a 32-byte sector, i.e. every sector of the line
+// would be hit by two separate L2 atomic requests.  The scratch therefore uses a permuted channel
+// order (channel 8j+4i+k of a head lives at float 16i+4j+k), so that reduction i of the 4 lanes
+// covers bytes [64i, 64i+64) of the line = two whole sectors, one request each.
+// cast_scratch_kernel undoes the permutation when it rounds to 16 bits.
 template <> struct GradScatter<__nv_bfloat16, float> {
     static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[8])
     {
         red_add_v4_f32_if(pred, p, w * go[0], w * go[1], w * go[2], w * go[3]);
-        red_add_v4_f32_if(pred, p + 16, w * go[4], w * go[5], w * go[6], w * go[7]);
+        red_add_v4_f32_if(pred, p + 64, w * go[4], w * go[5], w * go[6], w * go[7]);
     }
 };
 template <> struct GradScatter<__nv_bfloat16, __nv_bfloat16> {
@@ -651,9 +657,10 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     const int pix = M * kFastD;
     const int pixb = pix * static_cast<int>(sizeof(VT));
     const int gpixb = pix * static_cast<int>(sizeof(GT));
-    const int64_t lane_off = n * S * pix + m * kFastD + j * CPL;
-    const char *vlane = reinterpret_cast<const char *>(value + lane_off);
-    char *glane = reinterpret_cast<char *>(grad_value + lane_off);
+    const int64_t head_off = n * S * pix + m * kFastD;
+    const char *vlane = reinterpret_cast<const char *>(value + head_off + j * CPL);
+    // fp32 scratch of a 16-bit value type is channel-permuted (see GradScatter): lane j starts at float 4j
+    char *glane = reinterpret_cast<char *>(grad_value + head_off + (sizeof(GT) != sizeof(VT) ? j * 4 : j * CPL));
     int rowW[4];
     if (TCE) {
 #pragma unroll
@@ -747,14 +754,19 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 // --------------------------------------------------------------------------------------------
 // 16-bit grad_value epilogue: round the fp32 scratch once.
 // --------------------------------------------------------------------------------------------
-template <typename VT>
+template <typename VT, bool PERMUTED>
 __global__ void __launch_bounds__(256)
 cast_scratch_kernel(const float *__restrict__ src, VT *__restrict__ dst, int64_t n_vec8)
 {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec8; i += stride) {
-        const float4 a = __ldcs(reinterpret_cast<const float4 *>(src) + 2 * i);
-        const float4 b = __ldcs(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
+        // PERMUTED (fast-path scratch, 32-channel heads): output channels 8j..8j+7 of a head come from
+        // scratch floats [4j, 4j+4) and [16+4j, 16+4j+4) of that head's 32-float row.
+        const int64_t row = i >> 2;
+        const int j = static_cast<int>(i & 3);
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        const float4 a = __ldcs(PERMUTED ? s4 + row * 8 + j : s4 + 2 * i);
+        const float4 b = __ldcs(PERMUTED ? s4 + row * 8 + 4 + j : s4 + 2 * i + 1);
         const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         VT o[8];
 #pragma unroll

@@ -419,3 +419,41 @@ def test_frame_sharding_across_two_gpus(pkg, oracle):
         v, l, a = (x.to(d).contiguous() for x in sh.shard_frames(r, 2, inp["value"], inp["loc"], inp["aw"]))
         parts.append(pkg.MSDeformAttnFunction.apply(v, inp["shapes"].to(d), inp["lsi"].to(d), l, a, 64).cpu())
     assert torch.equal(torch.cat(parts, 0), whole.cpu())
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own CUDA extension, when its sm_100 build is present (tools/build_reference_cuda.py)
+# ------------------------------------------------------------------------------------------------
+def _reference_cuda():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "MSDA_reference_cuda.so")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("MSDA_reference_cuda", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("kind", ["model", "stress"])
+def test_against_reference_cuda_extension(pkg, oracle, kind):
+    """Same inputs through the reference's CUDA kernels (fp32, D = 32) and through ours."""
+    ref = _reference_cuda()
+    if ref is None:
+        pytest.skip("baseline/_ref/MSDA_reference_cuda.so not built")
+    levels = oracle.LEVELS_A
+    inp = oracle.make_inputs(kind, 5, levels, Lq=(None if kind == "model" else 700), seed=12)
+    t = dev_inputs(inp, torch.float32)
+    ext = pkg.load_extension()
+    args = (t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    out_r = ref.ms_deform_attn_forward(*args, 64, False)
+    out_o = ext.ms_deform_attn_forward(*args, 64, False)
+    gr = ref.ms_deform_attn_backward(*args, t["grad_out"], 64, False)
+    go = ext.ms_deform_attn_backward(*args, t["grad_out"], 64, False)
+    torch.cuda.synchronize()
+    assert oracle.max_rel(out_o.cpu(), out_r.cpu()) < 2e-6
+    assert oracle.max_rel(go[0].cpu(), gr[0].cpu()) < 2e-6       # grad_value (atomic order differs)
+    assert oracle.max_rel(go[2].cpu(), gr[2].cpu()) < 5e-6       # grad_attn_weight
+    # both are fp32: cell selection is identical (same h_im/w_im arithmetic), so no boundary masking
+    assert oracle.max_rel(go[1].cpu(), gr[1].cpu()) < 2e-5       # grad_sampling_loc

@@ -27,7 +27,17 @@ def main():
     ap.add_argument("--kinds", default="model,testpy")
     ap.add_argument("--dtypes", default="f32,bf16")
     ap.add_argument("--sets", type=int, default=3)
+    ap.add_argument("--reference", action="store_true",
+                    help="also time the reference's own CUDA extension (baseline/_ref/MSDA_reference_cuda.so, "
+                         "built by tools/build_reference_cuda.py; fp32 only)")
     args = ap.parse_args()
+    ref_ext = None
+    if args.reference:
+        import importlib.util
+        path = os.path.join(ROOT, "baseline", "_ref", "MSDA_reference_cuda.so")
+        spec = importlib.util.spec_from_file_location("MSDA_reference_cuda", path)
+        ref_ext = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref_ext)
     levels = {"A": O.LEVELS_A, "B": O.LEVELS_B, "C": O.LEVELS_C}[args.levels]
     dev = "cuda:0"
     ext = pkg.load_extension()
@@ -54,7 +64,11 @@ def main():
             def bwd(s):
                 return ext.ms_deform_attn_backward(s["v"], shapes, lsi, s["l"], s["a"], s["g"], 64, False)
 
-            for name, f, nbytes in (("fwd", fwd, bf), ("bwd", bwd, bb)):
+            passes = [("fwd", fwd, bf), ("bwd", bwd, bb)]
+            if ref_ext is not None and dt == "f32":
+                passes += [("ref-fwd", lambda s: ref_ext.ms_deform_attn_forward(s["v"], shapes, lsi, s["l"], s["a"], 64, False), bf),
+                           ("ref-bwd", lambda s: ref_ext.ms_deform_attn_backward(s["v"], shapes, lsi, s["l"], s["a"], s["g"], 64, False), bb)]
+            for name, f, nbytes in passes:
                 for i in range(3):
                     f(sets[i % len(sets)])
                 torch.cuda.synchronize()
@@ -65,7 +79,7 @@ def main():
                 ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
                 med = ts[len(ts) // 2]
                 qh = N * Lq * 8
-                print(f"{kind:7s} {dt:5s} {name}: median {med:8.1f} us  min {ts[0]:8.1f} us  "
+                print(f"{kind:7s} {dt:5s} {name:7s}: median {med:8.1f} us  min {ts[0]:8.1f} us  "
                       f"{qh / med / 1e3:6.2f} Gqh/s  {nbytes / med / 1e3:7.0f} GB/s algorithmic = {nbytes / med / 1e3 / peak * 100:5.1f}% of {peak:.0f}",
                       flush=True)
 
