@@ -86,8 +86,13 @@ int host_pipeline(msda_host_ctx *c, const msda_shape *shape, const void *value, 
             { cudaSetDevice(prev); return rc; }
     }
 
-    // chunking: up to 8 chunks, at least one frame each
-    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(d.N, 8));
+    // chunking: up to 16 chunks (MSDA_HOST_CHUNKS overrides, for tuning), at least one frame each
+    static const int64_t max_chunks = [] {
+        const char *e = std::getenv("MSDA_HOST_CHUNKS");
+        const long v = e ? std::atol(e) : 0;
+        return static_cast<int64_t>(v > 0 ? v : 16);
+    }();
+    const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(d.N, max_chunks));
     const int64_t per = (d.N + n_chunks - 1) / n_chunks;
     if ((rc = ctx_events(c, static_cast<size_t>(n_chunks)))) { cudaSetDevice(prev); return rc; }
 

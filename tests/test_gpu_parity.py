@@ -457,3 +457,46 @@ def test_against_reference_cuda_extension(pkg, oracle, kind):
     assert oracle.max_rel(go[2].cpu(), gr[2].cpu()) < 5e-6       # grad_attn_weight
     # both are fp32: cell selection is identical (same h_im/w_im arithmetic), so no boundary masking
     assert oracle.max_rel(go[1].cpu(), gr[1].cpu()) < 2e-5       # grad_sampling_loc
+
+
+# ------------------------------------------------------------------------------------------------
+# 64-bit addressing at the top of the scaling sweep (BASELINE.json config 5: N = 1024 at 512x896)
+# ------------------------------------------------------------------------------------------------
+def test_no_int32_overflow_at_1024_frames(capi, oracle):
+    """The reference's host code computes chunk offsets in int32 and overflows from frame 896 on at
+    this level set (ms_deform_attn_cuda.cu:62,84).  Here the element offset of the
+    last frame is 1023*9520*256 = 2.49e9 > 2^31: its result must equal the same frame computed alone."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~75 GB of free device memory")
+    levels = oracle.LEVELS_C
+    N, S, Lq = 1024, 9520, 9520
+    one = oracle.make_inputs("model", 1, levels, seed=13)
+    shapes, lsi = one["shapes"].to(DEV), one["lsi"].to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    value = torch.randn(N, S, 8, 32, device=DEV, generator=g)
+    # every frame uses the same locations / weights except the probed ones, which get their own
+    loc = one["loc"].to(DEV).expand(N, -1, -1, -1, -1, -1).contiguous()
+    aw = one["aw"].to(DEV).expand(N, -1, -1, -1, -1).contiguous()
+    go = torch.randn(N, Lq, 256, device=DEV, generator=g)
+    probes = [0, 895, 896, 959, 1023]
+    for i, n in enumerate(probes):
+        loc[n] = (loc[n] + 0.003 * (i + 1)).clamp(-0.2, 1.2)
+    out = capi.forward(value, shapes, lsi, loc, aw)
+    gv, gl, ga = capi.backward(value, shapes, lsi, loc, aw, go)
+    for n in probes:
+        sl = slice(n, n + 1)
+        o1 = capi.forward(value[sl].contiguous(), shapes, lsi, loc[sl].contiguous(), aw[sl].contiguous())
+        assert torch.equal(o1, out[sl]), n
+        gv1, gl1, ga1 = capi.backward(value[sl].contiguous(), shapes, lsi, loc[sl].contiguous(), aw[sl].contiguous(),
+                                      go[sl].contiguous())
+        assert torch.equal(gl1, gl[sl]) and torch.equal(ga1, ga[sl]), n
+        assert oracle.max_rel(gv1.cpu(), gv[sl].cpu()) < 5e-6, n      # fp32 atomics: summation order differs
+    # and one probed frame against the fp64 oracle
+    n = 1023
+    ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(value[n:n + 1].cpu().double(), one["shapes"], loc[n:n + 1].cpu().double(),
+                                                      aw[n:n + 1].cpu().double(), go[n:n + 1].cpu().double())
+    assert oracle.max_rel(out[n:n + 1].cpu(), ref_out) < FWD_TOL
+    assert oracle.max_rel(gv[n:n + 1].cpu(), rv) < GRAD_TOL
+    del value, loc, aw, go, out, gv, gl, ga
+    torch.cuda.empty_cache()

@@ -202,6 +202,18 @@ int main()
     CK(cudaMalloc(&rbuf, spans[2] * 128));
     CK(cudaMemset(rbuf, 0, spans[2] * 128));
     const int riters = 512;
+    // SM-side or L2-side limit?  Same kernel on a quarter / half / all of the SMs.
+    for (int frac = 4; frac >= 1; frac /= 2) {
+        const int c2 = ctas / frac;
+        const float ms = time_ms([&]() { red_kernel<0><<<c2, warps_per_cta * 32>>>(rbuf, spans[1], riters); });
+        const double lines = (double)c2 * warps_per_cta * riters * 4;
+        printf("RED.v4.f32 scattered, %3d CTAs (1/%d of the SMs x2): %7.2f Glines/s\n", c2, frac, lines / ms / 1e6);
+    }
+    for (int wpc = 4; wpc <= 32; wpc *= 2) {
+        const float ms = time_ms([&]() { red_kernel<0><<<sms, wpc * 32>>>(rbuf, spans[1], riters); });
+        const double lines = (double)sms * wpc * riters * 4;
+        printf("RED.v4.f32 scattered, 1 CTA/SM x %2d warps: %7.2f Glines/s\n", wpc, lines / ms / 1e6);
+    }
     for (int mode = 0; mode < 4; ++mode)
         for (int si = 0; si < 3; ++si) {
             auto run = [&]() {
