@@ -99,21 +99,6 @@ int         msda_check_im2col_step(int64_t n_frames, int im2col_step);
 /* Number of kernel launches issued by this library since load (for bench.py's
  * gpu_launches claim). */
 int64_t     msda_launch_count(void);
-/* Work scheduling of the D=32 fast kernels: -1 automatic (default), 0 one-shot grid
- * (warp i takes item i; what small decoder / FTF calls get), 1 persistent CTA per SM
- * over a contiguous raster slice of the queries, 2 persistent + 8-column strip order
- * (encoder self-attention, Lq == S).  Changes the order of the work only: forward
- * outputs, grad_sampling_loc and grad_attn_weight are bit-identical across modes.
- * A tuning / A-B measurement aid (the reference has no equivalent: it launches one
- * thread per output element, ms_deform_im2col_cuda.cuh:1249-1259).  Environment
- * variable MSDA_SCHED sets the process default.  Returns 0 or MSDA_E_UNSUPPORTED. */
-int         msda_set_schedule(int mode);
-/* Host evaluation of the strip order used by schedule 2 (the same inline function the
- * kernels call): order_out[i] = query processed at position i of a frame, for a
- * 4-level table given as HOST arrays.  Returns 1 if the strip order applies, 0 if the
- * table does not tile [0, S) (order_out is then the identity), <0 on error.  Test aid. */
-int         msda_strip_order(const int64_t *shapes_host, const int64_t *lsi_host, int64_t S,
-                             int32_t *order_out);
 
 /* ---- device-pointer operators --------------------------------------------------- */
 

@@ -31,8 +31,6 @@ PROTOTYPES = {
     "msda_algorithmic_bytes": (C.c_int64, [_SH, C.c_int]),
     "msda_check_im2col_step": (C.c_int, [C.c_int64, C.c_int]),
     "msda_launch_count": (C.c_int64, []),
-    "msda_set_schedule": (C.c_int, [C.c_int]),
-    "msda_strip_order": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "msda_forward": (C.c_int, [_SH, _P, _I64P, _I64P, _P, _P, _P, _P]),
     "msda_backward_workspace_bytes": (C.c_size_t, [_SH]),
     "msda_backward": (C.c_int, [_SH, _P, _I64P, _I64P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),

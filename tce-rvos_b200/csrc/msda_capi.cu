@@ -16,7 +16,6 @@
 namespace {
 
 std::atomic<int64_t> g_launches{0};
-std::atomic<int> g_sched{-1};          // msda_set_schedule(); -1 = automatic
 
 inline size_t dtype_size(int dt)
 {
@@ -99,41 +98,6 @@ unsigned generic_grid(int64_t warps, int threads)
     return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sms) * 32)));
 }
 
-int sm_count()
-{
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    return sms;
-}
-
-// Scheduling of the fast kernels (msda_kernels.cuh, "Work scheduling"):
-//   0 one-shot grid, 1 persistent CTA per SM over a raster slice, 2 persistent + strip swizzle.
-// MSDA_SCHED overrides the automatic choice (tuning / A-B measurements only).
-enum { SCHED_ONESHOT = 0, SCHED_PERSIST = 1, SCHED_PERSIST_SWZ = 2 };
-
-int pick_sched(const Dims &d, int persist_threads, int groups)
-{
-    static const int env_forced = [] {
-        const char *e = std::getenv("MSDA_SCHED");
-        return (e && *e) ? std::atoi(e) : -1;
-    }();
-    const int api_forced = g_sched.load();
-    const int forced = api_forced >= 0 ? api_forced : env_forced;
-    const bool tce = (d.M == 8 && d.P == 4 && d.L == 4);
-    if (!tce || d.Lq >= (int64_t(1) << 31)) return SCHED_ONESHOT;
-    const bool grid_like = (d.Lq == d.S) && d.S < (int64_t(1) << 30);
-    if (forced >= 0) return (forced == SCHED_PERSIST_SWZ && !grid_like) ? SCHED_PERSIST : forced;
-    // a persistent CTA needs a few iterations of work per SM to pay for its longer ramp
-    const int64_t per_iter = int64_t(sm_count()) * (persist_threads / 32 / groups);
-    if (d.N * d.Lq < 4 * per_iter) return SCHED_ONESHOT;
-    return grid_like ? SCHED_PERSIST_SWZ : SCHED_PERSIST;
-}
-
 // ---- forward ------------------------------------------------------------------------------
 
 template <typename VT, typename LT, bool PRO = false>
@@ -144,17 +108,6 @@ int launch_fwd_fast(const Dims &d, const void *value, const int64_t *shapes, con
     constexpr int HPW = 32 / msda::FastCfg<VT>::LPH;
     const int64_t items = d.N * d.Lq * (d.M / HPW);
     if (items == 0) return MSDA_OK;
-    constexpr int pthreads = msda::PersistCfg<VT>::FWD_THREADS;
-    const int sched = pick_sched(d, pthreads, 8 / HPW);
-    if (sched != SCHED_ONESHOT) {
-        auto kern = (sched == SCHED_PERSIST_SWZ) ? msda::fwd_fast_persist_kernel<VT, LT, PRO, true>
-                                                 : msda::fwd_fast_persist_kernel<VT, LT, PRO, false>;
-        kern<<<sm_count(), pthreads, 0, st>>>(
-            static_cast<const VT *>(value), shapes, lsi, static_cast<const LT *>(loc),
-            static_cast<const LT *>(aw), static_cast<VT *>(out), d.N * d.Lq, d.Lq, d.S, pro);
-        ++g_launches;
-        return launch_status();
-    }
     constexpr int threads = 256;
     auto kern = (d.M == 8 && d.P == 4) ? msda::fwd_fast_kernel<VT, LT, PRO, true> : msda::fwd_fast_kernel<VT, LT, PRO, false>;
     kern<<<grid_for_warps(items, threads), threads, 0, st>>>(
@@ -244,18 +197,6 @@ int launch_bwd_fast(const Dims &d, const void *value, const int64_t *shapes, con
     constexpr int HPW = 32 / msda::FastCfg<VT>::LPH;
     const int64_t items = d.N * d.Lq * (d.M / HPW);
     if (items == 0) return MSDA_OK;
-    constexpr int pthreads = msda::PersistCfg<VT>::BWD_THREADS;
-    const int sched = pick_sched(d, pthreads, 8 / HPW);
-    if (sched != SCHED_ONESHOT) {
-        auto pk = (sched == SCHED_PERSIST_SWZ) ? msda::bwd_fast_persist_kernel<VT, LT, GT, PRO, true>
-                                               : msda::bwd_fast_persist_kernel<VT, LT, GT, PRO, false>;
-        pk<<<sm_count(), pthreads, 0, st>>>(
-            static_cast<const VT *>(value), shapes, lsi, static_cast<const LT *>(loc),
-            static_cast<const LT *>(aw), static_cast<const VT *>(go), gv, static_cast<LT *>(gl),
-            static_cast<LT *>(ga), d.N * d.Lq, d.Lq, d.S, pro);
-        ++g_launches;
-        return launch_status();
-    }
     constexpr int threads = 256;
     auto kern = (d.M == 8 && d.P == 4) ? msda::bwd_fast_kernel<VT, LT, GT, PRO, true> : msda::bwd_fast_kernel<VT, LT, GT, PRO, false>;
     kern<<<grid_for_warps(items, threads), threads, 0, st>>>(
@@ -423,23 +364,6 @@ int msda_check_im2col_step(int64_t n_frames, int im2col_step)
 }
 
 int64_t msda_launch_count(void) { return g_launches.load(); }
-
-int msda_strip_order(const int64_t *shapes_host, const int64_t *lsi_host, int64_t S, int32_t *order_out)
-{
-    if (!shapes_host || !lsi_host || !order_out) return MSDA_E_NULL;
-    if (S <= 0 || S >= (int64_t(1) << 30)) return MSDA_E_SHAPE;
-    msda::StripMap sm;
-    msda::strip_map_fill(sm, shapes_host, lsi_host, S);
-    for (int64_t i = 0; i < S; ++i) order_out[i] = msda::strip_map_apply(sm, static_cast<int>(i));
-    return sm.ok ? 1 : 0;
-}
-
-int msda_set_schedule(int mode)
-{
-    if (mode < -1 || mode > SCHED_PERSIST_SWZ) return MSDA_E_UNSUPPORTED;
-    g_sched.store(mode);
-    return MSDA_OK;
-}
 
 int msda_forward(const msda_shape *shape, const void *value, const int64_t *shapes, const int64_t *lsi,
                  const void *loc, const void *aw, void *out, void *stream)

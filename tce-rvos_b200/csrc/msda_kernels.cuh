@@ -415,93 +415,30 @@ __device__ __forceinline__ void prologue_points(float (&xy)[2 * PPL], float (&a)
 }
 
 // --------------------------------------------------------------------------------------------
-// Work scheduling.
-//  * one-shot kernels: warp i of the grid takes item i (small calls: decoder / FTF shapes).
-//  * persistent kernels: ONE CTA per SM; CTA c owns the contiguous slice [Q*c/G, Q*(c+1)/G) of the
-//    N*Lq queries and walks it WPB/groups queries at a time, so everything that is resident on an
-//    SM at one moment — and everything that SM touched just before — belongs to neighbouring
-//    queries: the corner lines they share are L1 hits instead of L2 round trips.
-//    (The hardware block scheduler deals consecutive CTAs of a one-shot grid to DIFFERENT SMs,
-//    which is why the one-shot kernel measures a 62 % L1 hit rate at the encoder shape.)
-//  * SWZ (encoder self-attention, Lq == S, queries laid out like the value pixels): positions are
-//    mapped to queries through 8-pixel-wide vertical strips of each level, so a slice is a tall
-//    8-column tile instead of a thin raster band (more shared corners per L1 byte).  The map is a
-//    permutation of [0, Lq) whenever the level table tiles [0, S) — checked on the device — and the
-//    identity otherwise; it changes the order of the work only, never the result.
-// --------------------------------------------------------------------------------------------
-#ifndef MSDA_STRIP_W
-#define MSDA_STRIP_W 8
-#endif
-constexpr int kStripW = MSDA_STRIP_W;
-
-struct StripMap {
-    int start[4], H[4], W[4];
-    bool ok;
-};
-
-// The table lives in shared memory (13 words per CTA, filled once): keeping it in registers
-// across the persistent loop costs spills in the backward kernel.
-__host__ __device__ inline void strip_map_fill(StripMap &sm, const int64_t *shapes, const int64_t *lsi, int64_t S)
-{
-    int64_t expect = 0;
-    bool ok = true;
-    for (int l = 0; l < 4; ++l) {
-        const int64_t h = shapes[2 * l], w = shapes[2 * l + 1], st = lsi[l];
-        ok = ok && (st == expect) && h > 0 && w > 0;
-        expect = st + h * w;
-        sm.start[l] = static_cast<int>(st); sm.H[l] = static_cast<int>(h); sm.W[l] = static_cast<int>(w);
-    }
-    sm.ok = ok && (expect == S);
-}
-
-__device__ __forceinline__ void strip_map_load(StripMap &sm, const int64_t *__restrict__ shapes,
-                                               const int64_t *__restrict__ lsi, int64_t S)
-{
-    if (threadIdx.x == 0) strip_map_fill(sm, shapes, lsi, S);
-    __syncthreads();
-}
-
-// position inside a frame -> query index inside the frame
-__host__ __device__ inline int strip_map_apply(const StripMap &sm, int pos)
-{
-    if (!sm.ok) return pos;
-    int l = 0;
-#pragma unroll
-    for (int k = 1; k < 4; ++k) l = (pos >= sm.start[k]) ? k : l;
-    const int st = sm.start[l], H = sm.H[l], W = sm.W[l];
-    const int r = pos - st;
-    const int full = W / kStripW;
-    const int body = full * kStripW * H;
-    int row, col;
-    if (r < body) {
-        const int s = r / (kStripW * H), rr = r - s * (kStripW * H);
-        row = rr / kStripW; col = s * kStripW + (rr - row * kStripW);
-    } else {
-        const int rem = W - full * kStripW, r2 = r - body;
-        row = r2 / rem; col = full * kStripW + (r2 - row * rem);
-    }
-    return st + row * W + col;
-}
-
-// --------------------------------------------------------------------------------------------
 // FAST forward.  One warp = HPW heads of one (frame, query).
 //   item = nq * (M / HPW) + head_group
 // TCE = true fixes M = 8 heads, L = 4 levels, P = 4 points at compile time (TCE-RVOS / the
 // Deformable-DETR default): pixel and row strides become immediates / 4 per-level registers.
 // --------------------------------------------------------------------------------------------
 template <typename VT, typename LT, bool PROLOGUE, bool TCE>
-__device__ __forceinline__ void
-fwd_fast_item(const int64_t nq, const int64_t n, const int hg,
-              const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-              const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
-              const LT *__restrict__ aw, VT *__restrict__ out,
-              int64_t Lq, int64_t S, int M, int log2P, const ProArgs &pro)
+__global__ void __launch_bounds__(256, (sizeof(VT) == 4 ? MSDA_FWD_MIN_BLOCKS_F32 : MSDA_FWD_MIN_BLOCKS_BF16))
+fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
+                const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
+                const LT *__restrict__ aw, VT *__restrict__ out,
+                int64_t n_items, int64_t Lq, int64_t S, int M, int log2P, ProArgs pro)
 {
     using Cfg = FastCfg<VT>;
     constexpr int CPL = Cfg::CPL, LPH = Cfg::LPH, HPW = kWarp / LPH, PPL = kFastLP / LPH;
 
     const int lane = threadIdx.x & 31;
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (item >= n_items) return;   // warp-uniform
+
     if (TCE) { M = 8; log2P = 2; }
+    const int groups = M / HPW;
+    const int64_t nq = item / groups;
+    const int hg = static_cast<int>(item - nq * groups);
+    const int64_t n = nq / Lq;
     const int g = lane / LPH, j = lane % LPH;
     const int m = hg * HPW + g;
 
@@ -595,56 +532,6 @@ fwd_fast_item(const int64_t nq, const int64_t n, const int hg,
     VecIO<VT>::store_stream(out + (nq * M + m) * kFastD + j * CPL, acc);
 }
 
-template <typename VT, typename LT, bool PROLOGUE, bool TCE>
-__global__ void __launch_bounds__(256, (sizeof(VT) == 4 ? MSDA_FWD_MIN_BLOCKS_F32 : MSDA_FWD_MIN_BLOCKS_BF16))
-fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-                const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
-                const LT *__restrict__ aw, VT *__restrict__ out,
-                int64_t n_items, int64_t Lq, int64_t S, int M, int log2P, ProArgs pro)
-{
-    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (item >= n_items) return;   // warp-uniform
-    const int groups = (TCE ? 8 : M) / (kWarp / FastCfg<VT>::LPH);
-    const int64_t nq = item / groups;
-    fwd_fast_item<VT, LT, PROLOGUE, TCE>(nq, nq / Lq, static_cast<int>(item - nq * groups), value, shapes, lsi, loc, aw,
-                                         out, Lq, S, M, log2P, pro);
-}
-
-// persistent form: one CTA per SM (see "Work scheduling")
-template <typename VT> struct PersistCfg;
-template <> struct PersistCfg<float> { static constexpr int FWD_THREADS = 1024, BWD_THREADS = 768; };
-template <> struct PersistCfg<__nv_bfloat16> { static constexpr int FWD_THREADS = 768, BWD_THREADS = 512; };
-
-template <typename VT, typename LT, bool PROLOGUE, bool SWZ>
-__global__ void __launch_bounds__(PersistCfg<VT>::FWD_THREADS, 1)
-fwd_fast_persist_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-                        const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
-                        const LT *__restrict__ aw, VT *__restrict__ out,
-                        int64_t n_queries, int64_t Lq, int64_t S, ProArgs pro)
-{
-    constexpr int HPW = kWarp / FastCfg<VT>::LPH, groups = 8 / HPW;
-    // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the loop
-    // branch uniform and emits bare SHFLs inside it (otherwise every __shfl_sync in the body is
-    // wrapped in WARPSYNC / ENDCOLLECTIVE: +40 % instructions)
-    const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
-    const int qpi = static_cast<int>(blockDim.x >> 5) / groups;
-    const int64_t lo = n_queries * blockIdx.x / gridDim.x, hi = n_queries * (blockIdx.x + 1) / gridDim.x;
-    __shared__ StripMap sm;
-    if (SWZ) strip_map_load(sm, shapes, lsi, S);
-    const int lq = static_cast<int>(Lq);                     // the launcher guarantees Lq < 2^31
-    int64_t i = lo + warp / groups;
-    if (i >= hi) return;
-    int64_t n = i / Lq;
-    int pos = static_cast<int>(i - n * Lq);
-    for (; i < hi; i += qpi) {
-        const int q = SWZ ? strip_map_apply(sm, pos) : pos;
-        fwd_fast_item<VT, LT, PROLOGUE, true>(n * Lq + q, n, warp % groups, value, shapes, lsi, loc, aw, out,
-                                              Lq, S, 8, 2, pro);
-        pos += qpi;
-        while (pos >= lq) { pos -= lq; ++n; }
-    }
-}
-
 // --------------------------------------------------------------------------------------------
 // Transposing reduction over the LPH lanes of a head, done as a tree so that only a handful of
 // partial sums is ever live.  Lane jj owns points jj*PPL + pp.  tree<BIT, PBASE> returns, in every
@@ -724,19 +611,25 @@ template <> struct GradScatter<__nv_bfloat16, __nv_bfloat16> {
 // FAST backward.
 // --------------------------------------------------------------------------------------------
 template <typename VT, typename LT, typename GT, bool PROLOGUE, bool TCE>
-__device__ __forceinline__ void
-bwd_fast_item(const int64_t nq, const int64_t n, const int hg,
-              const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-              const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
-              const LT *__restrict__ aw, const VT *__restrict__ grad_out,
-              GT *__restrict__ grad_value, LT *__restrict__ grad_loc, LT *__restrict__ grad_aw,
-              int64_t Lq, int64_t S, int M, int log2P, const ProArgs &pro)
+__global__ void __launch_bounds__(256, (sizeof(VT) == 4 ? MSDA_BWD_MIN_BLOCKS_F32 : MSDA_BWD_MIN_BLOCKS_BF16))
+bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
+                const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
+                const LT *__restrict__ aw, const VT *__restrict__ grad_out,
+                GT *__restrict__ grad_value, LT *__restrict__ grad_loc, LT *__restrict__ grad_aw,
+                int64_t n_items, int64_t Lq, int64_t S, int M, int log2P, ProArgs pro)
 {
     using Cfg = FastCfg<VT>;
     constexpr int CPL = Cfg::CPL, LPH = Cfg::LPH, HPW = kWarp / LPH, PPL = kFastLP / LPH;
 
     const int lane = threadIdx.x & 31;
+    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (item >= n_items) return;
+
     if (TCE) { M = 8; log2P = 2; }
+    const int groups = M / HPW;
+    const int64_t nq = item / groups;
+    const int hg = static_cast<int>(item - nq * groups);
+    const int64_t n = nq / Lq;
     const int g = lane / LPH, j = lane % LPH;
     const int m = hg * HPW + g;
 
@@ -856,53 +749,6 @@ bwd_fast_item(const int64_t nq, const int64_t n, const int hg,
     }
     PointIO<LT, PPL>::store_loc(grad_loc + qh0 * (kFastLP * 2) + lane * (2 * PPL), gxy);
     PointIO<LT, PPL>::store_aw(grad_aw + qh0 * kFastLP + lane * PPL, ga);
-}
-
-template <typename VT, typename LT, typename GT, bool PROLOGUE, bool TCE>
-__global__ void __launch_bounds__(256, (sizeof(VT) == 4 ? MSDA_BWD_MIN_BLOCKS_F32 : MSDA_BWD_MIN_BLOCKS_BF16))
-bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-                const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
-                const LT *__restrict__ aw, const VT *__restrict__ grad_out,
-                GT *__restrict__ grad_value, LT *__restrict__ grad_loc, LT *__restrict__ grad_aw,
-                int64_t n_items, int64_t Lq, int64_t S, int M, int log2P, ProArgs pro)
-{
-    const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (item >= n_items) return;
-    const int groups = (TCE ? 8 : M) / (kWarp / FastCfg<VT>::LPH);
-    const int64_t nq = item / groups;
-    bwd_fast_item<VT, LT, GT, PROLOGUE, TCE>(nq, nq / Lq, static_cast<int>(item - nq * groups), value, shapes, lsi, loc,
-                                             aw, grad_out, grad_value, grad_loc, grad_aw, Lq, S, M, log2P, pro);
-}
-
-template <typename VT, typename LT, typename GT, bool PROLOGUE, bool SWZ>
-__global__ void __launch_bounds__(PersistCfg<VT>::BWD_THREADS, 1)
-bwd_fast_persist_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
-                        const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
-                        const LT *__restrict__ aw, const VT *__restrict__ grad_out,
-                        GT *__restrict__ grad_value, LT *__restrict__ grad_loc, LT *__restrict__ grad_aw,
-                        int64_t n_queries, int64_t Lq, int64_t S, ProArgs pro)
-{
-    constexpr int HPW = kWarp / FastCfg<VT>::LPH, groups = 8 / HPW;
-    // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the loop
-    // branch uniform and emits bare SHFLs inside it (otherwise every __shfl_sync in the body is
-    // wrapped in WARPSYNC / ENDCOLLECTIVE: +40 % instructions)
-    const int warp = __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0);
-    const int qpi = static_cast<int>(blockDim.x >> 5) / groups;
-    const int64_t lo = n_queries * blockIdx.x / gridDim.x, hi = n_queries * (blockIdx.x + 1) / gridDim.x;
-    __shared__ StripMap sm;
-    if (SWZ) strip_map_load(sm, shapes, lsi, S);
-    const int lq = static_cast<int>(Lq);                     // the launcher guarantees Lq < 2^31
-    int64_t i = lo + warp / groups;
-    if (i >= hi) return;
-    int64_t n = i / Lq;
-    int pos = static_cast<int>(i - n * Lq);
-    for (; i < hi; i += qpi) {
-        const int q = SWZ ? strip_map_apply(sm, pos) : pos;
-        bwd_fast_item<VT, LT, GT, PROLOGUE, true>(n * Lq + q, n, warp % groups, value, shapes, lsi, loc, aw, grad_out,
-                                                  grad_value, grad_loc, grad_aw, Lq, S, 8, 2, pro);
-        pos += qpi;
-        while (pos >= lq) { pos -= lq; ++n; }
-    }
 }
 
 // --------------------------------------------------------------------------------------------

@@ -286,9 +286,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("ms_deform_attn_prologue_forward", &ms_deform_attn_prologue_forward);
     m.def("ms_deform_attn_prologue_backward", &ms_deform_attn_prologue_backward);
     m.def("launch_count", []() { return msda_launch_count(); });
-    m.def("set_schedule", [](int mode) {
-        TORCH_CHECK(msda_set_schedule(mode) == 0, "set_schedule: mode must be -1 (auto), 0, 1 or 2");
-    });
     m.def("abi_version", []() { return msda_abi_version(); });
     m.attr("__b200_native__") = true;
 }

@@ -150,41 +150,3 @@ def test_drop_in_under_the_reference_module_name(pkg):
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         theirs(torch.zeros(1, 1, 256), torch.zeros(1, 1, 4, 2), torch.zeros(1, 4, 256),
                torch.tensor([[1, 1]] * 4), torch.tensor([0, 1, 2, 3]))
-
-
-def test_strip_order_is_a_permutation_with_tall_tiles(capi):
-    """Schedule 2 walks each level in 8-pixel-wide vertical strips (host evaluation of the inline
-    function the kernels call).  It must be a permutation of [0, S) for every level table that tiles
-    [0, S), keep each level's queries inside that level, and be the identity otherwise."""
-    import numpy as np
-    lib = capi.load()
-
-    def order(levels, lsi=None, S=None):
-        shapes = np.asarray(levels, dtype=np.int64)
-        if lsi is None:
-            lsi = np.concatenate([[0], np.cumsum(shapes.prod(1))[:-1]]).astype(np.int64)
-        S = int(shapes.prod(1).sum()) if S is None else S
-        out = np.empty(S, dtype=np.int32)
-        rc = lib.msda_strip_order(shapes.ctypes.data, np.ascontiguousarray(lsi).ctypes.data, S, out.ctypes.data)
-        return rc, out, lsi
-
-    for levels in ([(45, 80), (23, 40), (12, 20), (6, 10)], [(64, 112), (32, 56), (16, 28), (8, 14)],
-                   [(13, 21), (7, 11), (4, 6), (2, 3)], [(3, 5), (2, 3), (1, 2), (1, 1)], [(1, 1)] * 4):
-        rc, o, lsi = order(levels)
-        assert rc == 1
-        S = len(o)
-        assert np.array_equal(np.sort(o), np.arange(S)), levels
-        for l, (h, w) in enumerate(levels):
-            seg = o[lsi[l]:lsi[l] + h * w]
-            assert seg.min() == lsi[l] and seg.max() == lsi[l] + h * w - 1
-            # the first 8*h positions of a level wide enough are the 8 leftmost columns, row by row
-            if w >= 8:
-                rows, cols = np.divmod(seg[:8 * h] - lsi[l], w)
-                assert np.array_equal(cols, np.tile(np.arange(8), h)) and np.array_equal(rows, np.repeat(np.arange(h), 8))
-    # a table with a gap, and one whose sum is not S: identity, reported as inactive
-    lv = [(6, 10), (3, 5), (2, 3), (1, 2)]
-    lsi = np.array([0, 67, 82, 88], dtype=np.int64)
-    rc, o, _ = order(lv, lsi=lsi, S=90)
-    assert rc == 0 and np.array_equal(o, np.arange(90))
-    rc, o, _ = order(lv, S=100)
-    assert rc == 0 and np.array_equal(o, np.arange(100))

@@ -500,65 +500,3 @@ def test_no_int32_overflow_at_1024_frames(capi, oracle):
     assert oracle.max_rel(gv[n:n + 1].cpu(), rv) < GRAD_TOL
     del value, loc, aw, go, out, gv, gl, ga
     torch.cuda.empty_cache()
-
-
-# ------------------------------------------------------------------------------------------------
-# work scheduling (one-shot / persistent / persistent + strip order) never changes the result
-# ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("levels", [[(45, 80), (23, 40), (12, 20), (6, 10)],      # TCE level set A
-                                    [(13, 21), (7, 11), (4, 6), (2, 3)],         # ragged strips (W % 8 != 0)
-                                    [(3, 5), (2, 3), (1, 2), (1, 1)]])           # levels narrower than a strip
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_schedules_are_equivalent(capi, oracle, levels, dtype):
-    lib = capi.load()
-    N = 3
-    inp = oracle.make_inputs("model", N, levels, seed=21)
-    t = dev_inputs(inp, dtype, torch.float32)
-    res = {}
-    try:
-        for mode in (0, 1, 2):
-            assert lib.msda_set_schedule(mode) == 0
-            out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
-            gv, gl, ga = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
-            res[mode] = (out, gv, gl, ga)
-    finally:
-        lib.msda_set_schedule(-1)
-    for mode in (1, 2):
-        assert torch.equal(res[mode][0], res[0][0]), mode                      # forward: bitwise
-        assert torch.equal(res[mode][2], res[0][2]) and torch.equal(res[mode][3], res[0][3]), mode
-        tol = 5e-6 if dtype == torch.float32 else 2e-2                         # atomics: order differs
-        assert oracle.max_rel(res[mode][1].float().cpu(), res[0][1].float().cpu()) < tol, mode
-    # and against the fp64 oracle in the persistent + strip mode
-    if dtype == torch.float32:
-        ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(inp["value"].double(), inp["shapes"], inp["loc"].double(),
-                                                          inp["aw"].double(), inp["grad_out"].double())
-        assert oracle.max_rel(res[2][0].cpu(), ref_out) < FWD_TOL
-        check_grads(oracle, res[2][1:], (rv, rl, ra), inp["loc"], levels, GRAD_TOL)
-
-
-def test_strip_order_falls_back_when_the_level_table_does_not_tile_the_queries(capi, oracle):
-    """Lq == S but level_start_index is not the running sum of H*W (levels stored with a gap): the
-    strip map must degrade to the identity instead of skipping or duplicating queries."""
-    lib = capi.load()
-    levels = [(6, 10), (3, 5), (2, 3), (1, 2)]
-    S_packed = sum(h * w for h, w in levels)
-    gap = 7
-    inp = oracle.make_inputs("model", 2, levels, seed=5)
-    shapes = inp["shapes"].to(DEV)
-    lsi = inp["lsi"].clone()
-    lsi[1:] += gap                                      # levels 1.. start 7 pixels later
-    S = S_packed + gap
-    g = torch.Generator().manual_seed(9)
-    value = torch.randn(2, S, 8, 32, generator=g)
-    loc = torch.rand(2, S, 8, 4, 4, 2, generator=g)
-    aw = torch.softmax(torch.randn(2, S, 8, 16, generator=g), -1).view(2, S, 8, 4, 4)
-    outs = []
-    try:
-        for mode in (0, 2):
-            lib.msda_set_schedule(mode)
-            outs.append(capi.forward(value.to(DEV), shapes, lsi.to(DEV), loc.to(DEV), aw.to(DEV)))
-    finally:
-        lib.msda_set_schedule(-1)
-    assert torch.equal(outs[0], outs[1])
-    ref = oracle.c_forward(value.double(), inp["shapes"], lsi, loc.double(), aw.double())
-    assert oracle.max_rel(outs[1].cpu(), torch.as_tensor(ref).view_as(outs[1].cpu())) < FWD_TOL

@@ -27,8 +27,6 @@ def main():
     ap.add_argument("--kinds", default="model,testpy")
     ap.add_argument("--dtypes", default="f32,bf16")
     ap.add_argument("--sets", type=int, default=3)
-    ap.add_argument("--sched", default="-1", help="comma list of msda_set_schedule modes (-1 auto, 0 one-shot, 1 persistent, 2 persistent+strips)")
-    ap.add_argument("--passes", default="fwd,bwd")
     ap.add_argument("--reference", action="store_true",
                     help="also time the reference's own CUDA extension (baseline/_ref/MSDA_reference_cuda.so, "
                          "built by tools/build_reference_cuda.py; fp32 only)")
@@ -66,13 +64,11 @@ def main():
             def bwd(s):
                 return ext.ms_deform_attn_backward(s["v"], shapes, lsi, s["l"], s["a"], s["g"], 64, False)
 
-            passes = [p for p in [("fwd", fwd, bf), ("bwd", bwd, bb)] if p[0] in args.passes.split(",")]
+            passes = [("fwd", fwd, bf), ("bwd", bwd, bb)]
             if ref_ext is not None and dt == "f32":
                 passes += [("ref-fwd", lambda s: ref_ext.ms_deform_attn_forward(s["v"], shapes, lsi, s["l"], s["a"], 64, False), bf),
                            ("ref-bwd", lambda s: ref_ext.ms_deform_attn_backward(s["v"], shapes, lsi, s["l"], s["a"], s["g"], 64, False), bb)]
-            for sched, (name, f, nbytes) in [(sc, p) for sc in map(int, args.sched.split(",")) for p in passes]:
-                ext.set_schedule(-1 if name.startswith("ref") else sched)
-                name = f"{name}/s{sched}" if sched >= 0 else name
+            for name, f, nbytes in passes:
                 for i in range(3):
                     f(sets[i % len(sets)])
                 torch.cuda.synchronize()
@@ -83,7 +79,7 @@ def main():
                 ts = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
                 med = ts[len(ts) // 2]
                 qh = N * Lq * 8
-                print(f"{kind:7s} {dt:5s} {name:10s}: median {med:8.1f} us  min {ts[0]:8.1f} us  "
+                print(f"{kind:7s} {dt:5s} {name:7s}: median {med:8.1f} us  min {ts[0]:8.1f} us  "
                       f"{qh / med / 1e3:6.2f} Gqh/s  {nbytes / med / 1e3:7.0f} GB/s algorithmic = {nbytes / med / 1e3 / peak * 100:5.1f}% of {peak:.0f}",
                       flush=True)
 
