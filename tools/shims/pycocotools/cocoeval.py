@@ -1,0 +1,3 @@
+class COCOeval:
+    def __init__(self, *a, **k):
+        raise RuntimeError("pycocotools is not installed in this image (import shim)")
