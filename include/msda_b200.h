@@ -203,6 +203,37 @@ int msda_prologue_backward(const msda_shape *shape,
                            void *workspace, size_t workspace_bytes,
                            void *stream);
 
+/* ---- the two small passes either side of the sampling op ---- */
+
+/* Value epilogue (f2; models/ops/modules/ms_deform_attn.py:95-98): dst[r, :] = 0 where
+ * padding_mask[r] != 0, else convert(src[r, :]).  src / dst are [rows, width] (rows = N*S,
+ * width = M*D, a multiple of 8), dtypes MSDA_F32 or MSDA_BF16 in any combination (fp32 -> bf16
+ * feeds the 16-bit gather; bf16 -> fp32 with the same mask is its backward).  padding_mask is
+ * [rows] bool bytes or NULL.  dst may alias src when the dtypes agree.  Masked rows of src are
+ * not read. */
+int msda_value_epilogue(int64_t rows, int width,
+                        const void *src, int src_dtype,
+                        const uint8_t *padding_mask,
+                        void *dst, int dst_dtype,
+                        void *stream);
+
+/* Decoder sample selection (f3; models/tce_deformable_transformer.py:752-758): per (frame,
+ * query) the k largest of the M*L*P attention weights, in descending order, ties broken by
+ * the lower flat index (m, l, p) — torch.topk leaves that order unspecified — and the
+ * sampling locations of those points divided by valid_ratios[n, l, :] (NULL = no division).
+ *   sampling_loc [N, Lq, M, L, P, 2], attn_weight [N, Lq, M, L, P], valid_ratios [N, L, 2],
+ *   all in the shape's loc dtype (fp32 or bf16);  M*L*P <= 512, 1 <= k <= M*L*P
+ *   samples_keep [N, Lq, k, 2], weights_keep [N, Lq, k], index_keep [N, Lq, k] int64 or NULL.
+ * The value dtype / spatial size / channels of the shape are ignored. */
+int msda_topk_samples(const msda_shape *shape, int k,
+                      const void *sampling_loc,
+                      const void *attn_weight,
+                      const void *valid_ratios,
+                      void *samples_keep,
+                      void *weights_keep,
+                      int64_t *index_keep,
+                      void *stream);
+
 /* ---- host-buffer operators ---------------------------------------------------------
  * Same operators for a caller whose tensors live in HOST memory (pinned memory gives
  * full PCIe rate; pageable works).  spatial_shapes / level_start_index are HOST

@@ -154,6 +154,45 @@ def prologue(offsets, logits, reference_points, spatial_shapes):
 
 
 # ------------------------------------------------------------------------------------------------
+# rows f2 / f3: the passes either side of the op, restated with the reference's own torch calls
+# ------------------------------------------------------------------------------------------------
+def value_epilogue(value, padding_mask=None, out_dtype=None):
+    """models/ops/modules/ms_deform_attn.py:96-97 (+ the optional down-cast):
+    ``value.masked_fill(input_padding_mask[..., None], float(0))``."""
+    if padding_mask is not None:
+        value = value.masked_fill(padding_mask[..., None], float(0))
+    return value.to(out_dtype) if out_dtype is not None else value
+
+
+def decoder_sample_topk(sampling_locations, attention_weights, valid_ratios=None, k=30):
+    """models/tce_deformable_transformer.py:752-758, line for line, except that the selection is a
+    STABLE descending sort (ties -> lower index) where the reference calls topk, whose order among
+    equal weights is unspecified.  Returns (samples_keep, weights_keep, top_idx)."""
+    N, Len_q = sampling_locations.shape[:2]
+    if valid_ratios is not None:
+        sampling_locations = sampling_locations / valid_ratios[:, None, None, :, None, :]
+    weights_flat = attention_weights.reshape(N, Len_q, -1)
+    samples_flat = sampling_locations.reshape(N, Len_q, -1, 2)
+    top_idx = torch.sort(weights_flat.float(), dim=2, descending=True, stable=True)[1][..., :k]
+    weights_keep = torch.gather(weights_flat, 2, top_idx)
+    samples_keep = torch.gather(samples_flat, 2, top_idx.unsqueeze(-1).repeat(1, 1, 1, 2))
+    return samples_keep, weights_keep, top_idx
+
+
+def decoder_sample_topk_reference_calls(sampling_locations, attention_weights, valid_ratios, k=30):
+    """The same lines with the reference's literal torch.topk call (ties unspecified); used to pin the
+    restatement above wherever the k-th weight is unique."""
+    N, Len_q = sampling_locations.shape[:2]
+    sampling_locations = sampling_locations / valid_ratios[:, None, None, :, None, :]
+    weights_flat = attention_weights.view(N, Len_q, -1)
+    samples_flat = sampling_locations.view(N, Len_q, -1, 2)
+    top_weights, top_idx = weights_flat.topk(k, dim=2)
+    weights_keep = torch.gather(weights_flat, 2, top_idx)
+    samples_keep = torch.gather(samples_flat, 2, top_idx.unsqueeze(-1).repeat(1, 1, 1, 2))
+    return samples_keep, weights_keep, top_idx
+
+
+# ------------------------------------------------------------------------------------------------
 # seeded synthetic inputs (SURVEY.md 8d)
 # ------------------------------------------------------------------------------------------------
 def level_tensors(levels, device="cpu"):

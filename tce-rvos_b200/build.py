@@ -29,7 +29,7 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo"]   # no --use_fast_math: IEEE division / expf
 
 CAPI_SOURCES = ["msda_capi.cu"]
-CAPI_DEPS = ["msda_kernels.cuh", "msda_prologue_host.inl", "msda_host_pipeline.inl"]
+CAPI_DEPS = ["msda_kernels.cuh", "msda_prologue_host.inl", "msda_host_pipeline.inl", "msda_aux_kernels.cuh", "msda_aux_host.inl"]
 TORCH_SOURCES = ["msda_torch.cpp"]
 MODULE_NAME = "MultiScaleDeformableAttention_update"
 

@@ -31,6 +31,9 @@ PROTOTYPES = {
     "msda_algorithmic_bytes": (C.c_int64, [_SH, C.c_int]),
     "msda_check_im2col_step": (C.c_int, [C.c_int64, C.c_int]),
     "msda_launch_count": (C.c_int64, []),
+    "msda_value_epilogue": (C.c_int, [C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "msda_topk_samples": (C.c_int, [C.POINTER(msda_shape), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "msda_forward": (C.c_int, [_SH, _P, _I64P, _I64P, _P, _P, _P, _P]),
     "msda_backward_workspace_bytes": (C.c_size_t, [_SH]),
     "msda_backward": (C.c_int, [_SH, _P, _I64P, _I64P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
@@ -153,6 +156,50 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
                                 ws.data_ptr() if ws is not None else None, ws_bytes, _stream_ptr(value)),
               "msda_backward")
     return gv, gl, ga
+
+
+def value_epilogue(src, padding_mask=None, out_dtype=None, out=None):
+    """msda_value_epilogue on CUDA torch tensors: src [..., width] (fp32 / bf16), padding_mask
+    [...] bool or None -> masked (and converted) copy; out=src masks in place."""
+    import torch
+    lib = load()
+    if not src.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    width = src.shape[-1]
+    rows = src.numel() // width if width else 0
+    out_dtype = out_dtype or src.dtype
+    if out is None:
+        out = torch.empty(src.shape, dtype=out_dtype, device=src.device)
+    mask = None
+    if padding_mask is not None:
+        mask = padding_mask.contiguous().view(torch.uint8) if padding_mask.dtype == torch.bool else padding_mask.contiguous()
+        assert mask.numel() == rows and mask.dtype == torch.uint8
+    with torch.cuda.device(src.device):
+        check(lib.msda_value_epilogue(rows, width, src.data_ptr(), dtype_code(src.dtype),
+                                      mask.data_ptr() if mask is not None else None, out.data_ptr(),
+                                      dtype_code(out.dtype), _stream_ptr(src)), "msda_value_epilogue")
+    return out
+
+
+def topk_samples(sampling_loc, attn_weight, valid_ratios=None, k=30, want_index=True):
+    """msda_topk_samples on CUDA torch tensors -> (samples_keep [N,Lq,k,2], weights_keep [N,Lq,k],
+    index_keep [N,Lq,k] int64 or None)."""
+    import torch
+    lib = load()
+    if not sampling_loc.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    N, Lq, M, L, P, _ = sampling_loc.shape
+    sh = make_shape(N, 1, Lq, M, 1, L, P, MSDA_F32, dtype_code(sampling_loc.dtype))
+    samples = torch.empty(N, Lq, k, 2, dtype=sampling_loc.dtype, device=sampling_loc.device)
+    weights = torch.empty(N, Lq, k, dtype=attn_weight.dtype, device=sampling_loc.device)
+    index = torch.empty(N, Lq, k, dtype=torch.int64, device=sampling_loc.device) if want_index else None
+    with torch.cuda.device(sampling_loc.device):
+        check(lib.msda_topk_samples(C.byref(sh), int(k), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                                    valid_ratios.data_ptr() if valid_ratios is not None else None,
+                                    samples.data_ptr(), weights.data_ptr(),
+                                    index.data_ptr() if index is not None else None, _stream_ptr(sampling_loc)),
+              "msda_topk_samples")
+    return samples, weights, index
 
 
 # ---- host API on numpy arrays / pinned torch CPU tensors ---------------------------------------

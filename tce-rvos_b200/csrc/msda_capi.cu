@@ -84,8 +84,7 @@ inline unsigned grid_for_warps(int64_t warps, int threads)
     return static_cast<unsigned>((warps + wpb - 1) / wpb);
 }
 
-// grid for the grid-stride generic kernels: enough CTAs to fill the machine a few times over
-unsigned generic_grid(int64_t warps, int threads)
+int sm_count_aux()
 {
     static int sms = 0;
     if (!sms) {
@@ -94,6 +93,13 @@ unsigned generic_grid(int64_t warps, int threads)
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
+    return sms;
+}
+
+// grid for the grid-stride generic kernels: enough CTAs to fill the machine a few times over
+unsigned generic_grid(int64_t warps, int threads)
+{
+    const int sms = sm_count_aux();
     const int64_t need = (warps + threads / 32 - 1) / (threads / 32);
     return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sms) * 32)));
 }
@@ -423,3 +429,4 @@ int msda_backward_3d(const msda_shape *shape, int64_t frames_per_group, const vo
 
 #include "msda_prologue_host.inl"
 #include "msda_host_pipeline.inl"
+#include "msda_aux_host.inl"

@@ -275,6 +275,67 @@ std::vector<at::Tensor> ms_deform_attn_prologue_backward(const at::Tensor &value
     return {grad_value, grad_off, grad_logit};
 }
 
+// ---- rows f2 / f3 ---------------------------------------------------------------
+
+// models/ops/modules/ms_deform_attn.py:95-98: value.masked_fill(padding_mask[..., None], 0), optionally
+// converted to `out_dtype`; in_place reuses the input's storage (dtypes must agree).
+at::Tensor ms_deform_attn_value_epilogue(const at::Tensor &src, const c10::optional<at::Tensor> &padding_mask,
+                                         at::ScalarType out_dtype, bool in_place)
+{
+    TORCH_CHECK(src.is_cuda(), "Not implemented on the CPU");
+    TORCH_CHECK(src.is_contiguous(), "value tensor has to be contiguous");
+    TORCH_CHECK(src.dim() >= 2, "value must be [..., width]");
+    const int64_t width = src.size(-1);
+    const int64_t rows = width ? src.numel() / width : 0;
+    TORCH_CHECK(!in_place || out_dtype == src.scalar_type(), "in_place needs out_dtype == value dtype");
+    const uint8_t *mask = nullptr;
+    at::Tensor mask_c;
+    if (padding_mask.has_value() && padding_mask->defined()) {
+        TORCH_CHECK(padding_mask->is_cuda() && padding_mask->numel() == rows, "padding_mask must be a CUDA tensor with one entry per row");
+        TORCH_CHECK(padding_mask->scalar_type() == at::kBool || padding_mask->scalar_type() == at::kByte, "padding_mask must be bool");
+        mask_c = padding_mask->contiguous();
+        mask = static_cast<const uint8_t *>(mask_c.data_ptr());
+    }
+    const c10::cuda::CUDAGuard guard(src.device());
+    at::Tensor dst = in_place ? src : at::empty(src.sizes(), src.options().dtype(out_dtype));
+    const int rc = msda_value_epilogue(rows, static_cast<int>(width), src.data_ptr(), dtype_code(src.scalar_type(), "value"), mask,
+                                       dst.data_ptr(), dtype_code(out_dtype, "out_dtype"), stream_of(src));
+    check_rc(rc, "ms_deform_attn_value_epilogue");
+    return dst;
+}
+
+// models/tce_deformable_transformer.py:752-758 -> (samples_keep, weights_keep, top_idx)
+std::vector<at::Tensor> ms_deform_attn_topk_samples(const at::Tensor &sampling_loc, const at::Tensor &attn_weight,
+                                                    const c10::optional<at::Tensor> &valid_ratios, int64_t k)
+{
+    TORCH_CHECK(sampling_loc.is_cuda() && attn_weight.is_cuda(), "Not implemented on the CPU");
+    TORCH_CHECK(sampling_loc.is_contiguous() && attn_weight.is_contiguous(), "sampling_loc / attn_weight have to be contiguous");
+    TORCH_CHECK(sampling_loc.dim() == 6 && sampling_loc.size(5) == 2, "sampling_loc must be [N, Lq, M, L, P, 2]");
+    TORCH_CHECK(attn_weight.numel() * 2 == sampling_loc.numel(), "attn_weight must be [N, Lq, M, L, P]");
+    TORCH_CHECK(sampling_loc.scalar_type() == attn_weight.scalar_type(), "sampling_loc and attn_weight must share a dtype");
+    msda_shape s{};
+    s.n_frames = sampling_loc.size(0); s.n_queries = sampling_loc.size(1);
+    s.n_heads = static_cast<int32_t>(sampling_loc.size(2)); s.n_levels = static_cast<int32_t>(sampling_loc.size(3));
+    s.n_points = static_cast<int32_t>(sampling_loc.size(4));
+    s.spatial_size = 1; s.channels = 1; s.value_dtype = MSDA_F32;
+    s.loc_dtype = dtype_code(sampling_loc.scalar_type(), "sampling_loc");
+    const void *vr = nullptr;
+    at::Tensor vr_c;
+    if (valid_ratios.has_value() && valid_ratios->defined()) {
+        TORCH_CHECK(valid_ratios->is_cuda() && valid_ratios->numel() == s.n_frames * s.n_levels * 2, "valid_ratios must be [N, L, 2]");
+        vr_c = valid_ratios->to(sampling_loc.scalar_type()).contiguous();
+        vr = vr_c.data_ptr();
+    }
+    const c10::cuda::CUDAGuard guard(sampling_loc.device());
+    at::Tensor samples = at::empty({s.n_frames, s.n_queries, k, 2}, sampling_loc.options());
+    at::Tensor weights = at::empty({s.n_frames, s.n_queries, k}, attn_weight.options());
+    at::Tensor index = at::empty({s.n_frames, s.n_queries, k}, sampling_loc.options().dtype(at::kLong));
+    const int rc = msda_topk_samples(&s, static_cast<int>(k), sampling_loc.data_ptr(), attn_weight.data_ptr(), vr,
+                                     samples.data_ptr(), weights.data_ptr(), index.data_ptr<int64_t>(), stream_of(sampling_loc));
+    check_rc(rc, "ms_deform_attn_topk_samples");
+    return {samples, weights, index};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
 {
     m.doc() = "B200-native (sm_100a) multi-scale deformable attention; drop-in for TCE-RVOS models/ops";
@@ -285,6 +346,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("ms_deform_attn_prologue_supported", &ms_deform_attn_prologue_supported);
     m.def("ms_deform_attn_prologue_forward", &ms_deform_attn_prologue_forward);
     m.def("ms_deform_attn_prologue_backward", &ms_deform_attn_prologue_backward);
+    m.def("ms_deform_attn_value_epilogue", &ms_deform_attn_value_epilogue);
+    m.def("ms_deform_attn_topk_samples", &ms_deform_attn_topk_samples);
     m.def("launch_count", []() { return msda_launch_count(); });
     m.def("abi_version", []() { return msda_abi_version(); });
     m.attr("__b200_native__") = true;

@@ -2,5 +2,8 @@
 from .ms_deform_attn_func import MSDeformAttnFunction
 from .ms_deform_attn_func import MSDeformAttnFunction3D
 from .ms_deform_attn_func import MSDeformAttnPrologueFunction
+from .ms_deform_attn_func import MSDeformAttnValueEpilogue
+from .ms_deform_attn_func import decoder_sample_topk
 
-__all__ = ["MSDeformAttnFunction", "MSDeformAttnFunction3D", "MSDeformAttnPrologueFunction"]
+__all__ = ["MSDeformAttnFunction", "MSDeformAttnFunction3D", "MSDeformAttnPrologueFunction",
+           "MSDeformAttnValueEpilogue", "decoder_sample_topk"]

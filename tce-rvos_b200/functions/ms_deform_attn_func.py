@@ -7,7 +7,10 @@ The reference's third member, ms_deform_attn_core_pytorch (:67-87, "for debug an
 is NOT shipped in the product package: it is test infrastructure and lives in oracle/.
 
 New here: MSDeformAttnPrologueFunction, which fuses the module's softmax + location prologue
-(models/ops/modules/ms_deform_attn.py:99-109) into the gather kernel.
+(models/ops/modules/ms_deform_attn.py:99-109) into the gather kernel; MSDeformAttnValueEpilogue, the
+masked_fill (+ optional bf16 down-cast) that follows value_proj (:95-98) as one pass; and
+decoder_sample_topk, the decoder's top-30 sample selection (models/tce_deformable_transformer.py:752-758)
+as one launch.
 """
 from __future__ import annotations
 
@@ -103,3 +106,43 @@ class MSDeformAttnPrologueFunction(Function):
             grad_output.contiguous(), bool(need_ref))
         grad_ref = grads[3] if need_ref else None
         return grads[0], None, None, grads[1], grads[2], grad_ref, None
+
+
+class MSDeformAttnValueEpilogue(Function):
+    """value_proj output -> value the sampling kernels read: rows under the padding mask become zero
+    (models/ops/modules/ms_deform_attn.py:96-97) and the tensor is optionally stored as bf16, in ONE
+    pass.  Backward is the same pass on the incoming gradient (same mask, conversion back)."""
+
+    @staticmethod
+    def forward(ctx, value, padding_mask=None, out_dtype=None):
+        MSDA = _load_ext()
+        out_dtype = out_dtype or value.dtype
+        ctx.in_dtype = value.dtype
+        ctx.save_for_backward(padding_mask if padding_mask is not None else torch.empty(0, device=value.device))
+        ctx.has_mask = padding_mask is not None
+        return MSDA.ms_deform_attn_value_epilogue(value.contiguous(), padding_mask, out_dtype, False)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        MSDA = _load_ext()
+        (mask,) = ctx.saved_tensors
+        grad = MSDA.ms_deform_attn_value_epilogue(grad_output.contiguous(), mask if ctx.has_mask else None,
+                                                  ctx.in_dtype, False)
+        return grad, None, None
+
+
+def decoder_sample_topk(sampling_locations, attention_weights, valid_ratios=None, k=30):
+    """(samples_keep [N,Lq,k,2], weights_keep [N,Lq,k], top_idx [N,Lq,k]) as computed by the decoder
+    loop of the reference (models/tce_deformable_transformer.py:752-758):
+
+        sampling_locations / valid_ratios[:, None, None, :, None, :]
+        top_weights, top_idx = weights_flat.topk(k, dim=2); gather(weights), gather(samples)
+
+    One launch; not differentiable (the reference never back-propagates through these tensors:
+    they leave the transformer as `inter_samples` and are dropped, models/tce_rvos.py:312).  Equal
+    weights are ordered by the lower (head, level, point) index."""
+    MSDA = _load_ext()
+    with torch.no_grad():
+        return tuple(MSDA.ms_deform_attn_topk_samples(sampling_locations.contiguous(), attention_weights.contiguous(),
+                                                      valid_ratios, int(k)))

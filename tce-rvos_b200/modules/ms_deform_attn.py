@@ -15,6 +15,10 @@ What differs:
     raw Linear outputs.  The returned sampling_locations / attention_weights are then materialised
     by the kernel only when ``return_sampling`` is True (the decoder needs them,
     tce_deformable_transformer.py:752-758; encoder and FTF discard them) and carry no gradient.
+  * ``fused_value_epilogue`` (default False): the masked_fill of :96-97 runs as one pass of the
+    extension instead of an out-of-place torch op, and with ``value_dtype = torch.bfloat16`` the same
+    pass stores the value as bf16 so that the 16-bit gather kernels are used (bf16 value and output,
+    fp32 locations and weights; 1e-2 accuracy class).
 """
 from __future__ import annotations
 
@@ -26,7 +30,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction, MSDeformAttnPrologueFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnPrologueFunction, MSDeformAttnValueEpilogue
 from .._ext import load as _load_ext
 
 
@@ -61,6 +65,8 @@ class MSDeformAttn(nn.Module):
         # B200 additions (not parameters, not in state_dict)
         self.fused_prologue = False
         self.return_sampling = True
+        self.fused_value_epilogue = False
+        self.value_dtype = None             # None = keep value_proj's dtype | torch.bfloat16
         self.check_shapes = "once"          # True | False | "once"
         self._checked = set()
 
@@ -107,7 +113,9 @@ class MSDeformAttn(nn.Module):
         self._validate_shapes(input_spatial_shapes, Len_in)
 
         value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
+        if self.fused_value_epilogue and value.is_cuda and (input_padding_mask is not None or self.value_dtype is not None):
+            value = MSDeformAttnValueEpilogue.apply(value, input_padding_mask, self.value_dtype)
+        elif input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         sampling_offsets = self.sampling_offsets(query).view(
@@ -129,7 +137,7 @@ class MSDeformAttn(nn.Module):
                     output, sampling_locations, attention_weights = res
                 else:
                     output, sampling_locations, attention_weights = res, None, None
-                return self.output_proj(output), sampling_locations, attention_weights
+                return self.output_proj(output.to(query.dtype)), sampling_locations, attention_weights
 
         attention_weights = F.softmax(attention_weights, -1).view(
             N, Len_q, self.n_heads, self.n_levels, self.n_points)
@@ -143,5 +151,5 @@ class MSDeformAttn(nn.Module):
         output = MSDeformAttnFunction.apply(
             value, input_spatial_shapes, input_level_start_index, sampling_locations, attention_weights,
             self.im2col_step)
-        output = self.output_proj(output)
+        output = self.output_proj(output.to(query.dtype))
         return output, sampling_locations, attention_weights

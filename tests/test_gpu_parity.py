@@ -500,3 +500,114 @@ def test_no_int32_overflow_at_1024_frames(capi, oracle):
     assert oracle.max_rel(gv[n:n + 1].cpu(), rv) < GRAD_TOL
     del value, loc, aw, go, out, gv, gl, ga
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------
+# row f2: value epilogue (masked_fill + optional conversion), ms_deform_attn.py:95-98
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("src_dt,dst_dt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                           (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("width", [256, 24])
+def test_value_epilogue_is_bit_exact(capi, oracle, src_dt, dst_dt, width):
+    g = torch.Generator().manual_seed(3)
+    N, S = 3, 4820 if width == 256 else 37
+    v = torch.randn(N, S, width, generator=g).to(src_dt)
+    v[0, 5, 3] = float("inf")                       # a masked row is never read: inf must not leak as NaN
+    m = torch.rand(N, S, generator=g) < 0.25
+    m[0, 5] = True
+    ref = oracle.value_epilogue(v, m, dst_dt)
+    got = capi.value_epilogue(v.to(DEV), m.to(DEV), dst_dt)
+    assert got.dtype == dst_dt and torch.equal(got.cpu(), ref)
+    # no mask: pure conversion / copy
+    v[0, 5, 3] = 1.0
+    assert torch.equal(capi.value_epilogue(v.to(DEV), None, dst_dt).cpu(), oracle.value_epilogue(v, None, dst_dt))
+    if src_dt == dst_dt:                             # in place
+        d = v.to(DEV)
+        assert capi.value_epilogue(d, m.to(DEV), out=d).data_ptr() == d.data_ptr()
+        assert torch.equal(d.cpu(), oracle.value_epilogue(v, m))
+    assert capi.value_epilogue(v[:0].to(DEV), None, dst_dt).numel() == 0
+
+
+def test_value_epilogue_autograd_and_module(pkg, oracle):
+    g = torch.Generator().manual_seed(4)
+    N, S = 2, 391
+    x = torch.randn(N, S, 256, generator=g)
+    m = torch.rand(N, S, generator=g) < 0.2
+    go = torch.randn(N, S, 256, generator=g)
+    for dt in (torch.float32, torch.bfloat16):
+        a = x.clone().requires_grad_(True)
+        oracle.value_epilogue(a, m, dt).backward(go.to(dt))
+        b = x.to(DEV).requires_grad_(True)
+        pkg.MSDeformAttnValueEpilogue.apply(b, m.to(DEV), dt).backward(go.to(DEV, dt))
+        assert torch.equal(b.grad.cpu(), a.grad), dt
+    # module: the fused pass gives the reference composition's result exactly in fp32 ...
+    levels = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in levels)
+    shapes, lsi = oracle.level_tensors(levels, DEV)
+    torch.manual_seed(0)
+    mod = pkg.MSDeformAttn().to(DEV)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.01); mod.attention_weights.weight.normal_(0, 0.1)
+    q = torch.randn(2, S, 256, generator=g).to(DEV)
+    src = torch.randn(2, S, 256, generator=g).to(DEV)
+    ref_pts = oracle.reference_points_grid(levels)[None, :, None, :].expand(2, S, 4, 2).contiguous().to(DEV)
+    pm = (torch.rand(2, S, generator=g) < 0.15).to(DEV)
+    base = mod(q, ref_pts, src, shapes, lsi, pm)[0]
+    mod.fused_value_epilogue = True
+    fused = mod(q, ref_pts, src, shapes, lsi, pm)[0]
+    assert torch.equal(base, fused)
+    # ... and within the bf16 tolerance with a 16-bit value
+    mod.value_dtype = torch.bfloat16
+    low = mod(q, ref_pts, src, shapes, lsi, pm)[0]
+    assert low.dtype == torch.float32 and oracle.max_rel(low.cpu(), base.cpu()) < BF16_TOL
+    low.sum().backward()
+    assert mod.value_proj.weight.grad is not None and torch.isfinite(mod.value_proj.weight.grad).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# row f3: decoder sample selection, tce_deformable_transformer.py:752-758
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,Lq,M,L,P,k", [(36, 5, 8, 4, 4, 30),      # TCE decoder at inference (36 frames, 5 queries)
+                                          (10, 5, 8, 4, 4, 30),      # training clip
+                                          (2, 301, 8, 4, 4, 30),
+                                          (3, 9, 2, 4, 4, 30),       # 32 candidates
+                                          (3, 9, 3, 4, 4, 7),        # 48 candidates: padded sort
+                                          (2, 5, 8, 4, 16, 100),     # 512 candidates
+                                          (2, 5, 8, 4, 4, 1), (2, 5, 8, 4, 4, 128)])
+def test_decoder_sample_topk_is_bit_exact(pkg, capi, oracle, N, Lq, M, L, P, k):
+    g = torch.Generator().manual_seed(N * 1000 + Lq)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.4 - 0.2
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    vr = 0.5 + 0.5 * torch.rand(N, L, 2, generator=g)
+    rs, rw, ri = oracle.decoder_sample_topk(loc, aw, vr, k)
+    s, w, i = capi.topk_samples(loc.to(DEV), aw.to(DEV), vr.to(DEV), k)
+    assert torch.equal(i.cpu(), ri) and torch.equal(w.cpu(), rw) and torch.equal(s.cpu(), rs)
+    s2, w2, i2 = pkg.decoder_sample_topk(loc.to(DEV), aw.to(DEV), vr.to(DEV), k)     # torch binding, same entry point
+    assert torch.equal(i2, i) and torch.equal(w2, w) and torch.equal(s2, s)
+    # no valid_ratios = no division
+    s3, _, _ = capi.topk_samples(loc.to(DEV), aw.to(DEV), None, k)
+    assert torch.equal(s3.cpu(), oracle.decoder_sample_topk(loc, aw, None, k)[0])
+
+
+def test_decoder_sample_topk_ties_and_bf16(capi, oracle):
+    g = torch.Generator().manual_seed(8)
+    N, Lq = 4, 5
+    loc = torch.rand(N, Lq, 8, 4, 4, 2, generator=g)
+    vr = 0.5 + 0.5 * torch.rand(N, 4, 2, generator=g)
+    # the model at initialisation: every weight is 1/16 (ms_deform_attn.py:72-73) -> the first 30 candidates
+    flat = torch.full((N, Lq, 8, 4, 4), 1.0 / 16)
+    s, w, i = capi.topk_samples(loc.to(DEV), flat.to(DEV), vr.to(DEV), 30)
+    rs, rw, ri = oracle.decoder_sample_topk(loc, flat, vr, 30)
+    assert torch.equal(i.cpu(), ri) and torch.equal(s.cpu(), rs) and torch.equal(w.cpu(), rw)
+    # groups of equal weights, negative weights, and a bf16 run (many exact ties by construction)
+    aw = (torch.randint(-3, 4, (N, Lq, 8, 4, 4), generator=g).float() / 8)
+    s, w, i = capi.topk_samples(loc.to(DEV), aw.to(DEV), vr.to(DEV), 30)
+    rs, rw, ri = oracle.decoder_sample_topk(loc, aw, vr, 30)
+    assert torch.equal(i.cpu(), ri) and torch.equal(s.cpu(), rs) and torch.equal(w.cpu(), rw)
+    lb, ab, vb = loc.bfloat16(), torch.softmax(torch.randn(N, Lq, 8, 16, generator=g), -1).view(N, Lq, 8, 4, 4).bfloat16(), vr.bfloat16()
+    s, w, i = capi.topk_samples(lb.to(DEV), ab.to(DEV), vb.to(DEV), 30)
+    ri = oracle.decoder_sample_topk(lb, ab, vb, 30)[2]
+    assert torch.equal(i.cpu(), ri) and torch.equal(w.cpu(), torch.gather(ab.view(N, Lq, -1), 2, ri))
+    ref_s = torch.gather((lb.float() / vb.float()[:, None, None, :, None, :]).bfloat16().view(N, Lq, -1, 2), 2,
+                         ri.unsqueeze(-1).repeat(1, 1, 1, 2))
+    assert torch.equal(s.cpu(), ref_s)

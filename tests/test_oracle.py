@@ -133,3 +133,37 @@ def test_oracle_3d_backward_against_finite_differences(oracle):
         vp[idx] += eps; vm[idx] -= eps
         num = (f(vp, loc, inp["aw"]) - f(vm, loc, inp["aw"])) / (2 * eps)
         assert abs(num - gv[idx]) < 1e-6 * max(1.0, abs(num))
+
+
+# ------------------------------------------------------------------------------------------------
+# rows f2 / f3: the restatements of the passes either side of the op
+# ------------------------------------------------------------------------------------------------
+def test_decoder_sample_topk_restatement_matches_the_reference_calls(oracle):
+    """models/tce_deformable_transformer.py:752-758 with its literal torch.topk vs the stable-sort
+    restatement the CUDA kernel is checked against: identical wherever weights are distinct (softmax of
+    random logits), and for all-equal weights (the model at initialisation: attention_weights.weight = 0,
+    ms_deform_attn.py:72-73) the restatement picks the first k candidates."""
+    g = torch.Generator().manual_seed(0)
+    N, Lq, M, L, P = 3, 7, 8, 4, 4
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g)
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    vr = 0.5 + 0.5 * torch.rand(N, L, 2, generator=g)
+    s1, w1, i1 = oracle.decoder_sample_topk(loc, aw, vr, 30)
+    s2, w2, i2 = oracle.decoder_sample_topk_reference_calls(loc, aw, vr, 30)
+    assert torch.equal(w1, w2) and torch.equal(i1, i2) and torch.equal(s1, s2)
+    assert s1.shape == (N, Lq, 30, 2) and w1.shape == (N, Lq, 30)
+    assert bool((w1[..., :-1] >= w1[..., 1:]).all())
+    flat = torch.full((N, Lq, M, L, P), 1.0 / 16)
+    s3, w3, i3 = oracle.decoder_sample_topk(loc, flat, vr, 30)
+    assert torch.equal(i3, torch.arange(30).expand(N, Lq, 30))
+    assert torch.equal(s3, (loc / vr[:, None, None, :, None, :]).reshape(N, Lq, -1, 2)[:, :, :30])
+
+
+def test_value_epilogue_restatement(oracle):
+    g = torch.Generator().manual_seed(1)
+    v = torch.randn(2, 11, 256, generator=g)
+    m = torch.rand(2, 11, generator=g) < 0.3
+    out = oracle.value_epilogue(v, m)
+    assert torch.equal(out[m], torch.zeros_like(out[m])) and torch.equal(out[~m], v[~m])
+    assert oracle.value_epilogue(v, m, torch.bfloat16).dtype == torch.bfloat16
+    assert torch.equal(oracle.value_epilogue(v), v)
