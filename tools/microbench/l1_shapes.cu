@@ -54,6 +54,15 @@ __global__ void ld_kernel(const float *__restrict__ buf, float *out, int window_
             const int line = r & (window_lines - 1);
             const float4 v = __ldg(reinterpret_cast<const float4 *>(base + line * 128) + (lane & 7));
             acc += v.x + v.y + v.z + v.w;
+        } else if (MODE == 6) {
+            // LDG.256: 4 lanes x 32 B cover a line, 8 DIFFERENT lines per warp instruction
+            const int g = lane >> 2;
+            const int line = (r + g * 7) & (window_lines - 1);
+            float a, b, c, d, e, f, gg, h;
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(a), "=f"(b), "=f"(c), "=f"(d), "=f"(e), "=f"(f), "=f"(gg), "=f"(h)
+                         : "l"(base + line * 128 + (lane & 3) * 32));
+            acc += a + b + c + d + e + f + gg + h;
         }
     }
     if (acc == 123.456f) out[0] = acc;
@@ -138,7 +147,7 @@ float time_ms(F f)
     return ms;
 }
 
-int main()
+int main(int argc, char **argv)
 {
     int dev = 0, sms = 0, khz = 0;
     CK(cudaGetDevice(&dev));
@@ -148,16 +157,19 @@ int main()
     const double ghz = khz / 1e6;
 
     const int warps_per_cta = 16, ctas = sms * 2;             // 32 warps / SM
-    const int window = 32;                                     // lines per warp: 4 KB -> 128 KB / SM in L1
+    // lines per warp: 32 -> 4 KB/warp = 128 KB/SM, L1 resident; argv[1] = 256 -> 1 MB/SM: served by the L2
+    const int window = argc > 1 ? atoi(argv[1]) : 32;
+    const bool loads_only = argc > 1;
     float *buf, *out;
     const size_t nwarps = (size_t)ctas * warps_per_cta;
     CK(cudaMalloc(&buf, nwarps * window * 128));
     CK(cudaMemset(buf, 0, nwarps * window * 128));
     CK(cudaMalloc(&out, 4));
-    const char *names[6] = {"LDG.32  1 line/instr", "LDG.128 4 scattered lines (fp32 layout)", "LDG.128 4 contiguous lines",
-                            "LDG.64  2 scattered lines", "LDG.128 8 scattered half-lines (bf16 layout)", "LDG.128 same line x4 quarters"};
-    const int lines_per[6] = {1, 4, 4, 2, 8, 1};
-    for (int mode = 0; mode < 6; ++mode) {
+    const char *names[7] = {"LDG.32  1 line/instr", "LDG.128 4 scattered lines (fp32 layout)", "LDG.128 4 contiguous lines",
+                            "LDG.64  2 scattered lines", "LDG.128 8 scattered half-lines (bf16 layout)", "LDG.128 same line x4 quarters",
+                            "LDG.256 8 scattered lines (4 lanes x 32 B)"};
+    const int lines_per[7] = {1, 4, 4, 2, 8, 1, 8};
+    for (int mode = 0; mode < 7; ++mode) {
         auto run = [&]() {
             switch (mode) {
                 case 0: ld_kernel<0><<<ctas, warps_per_cta * 32>>>(buf, out, window); break;
@@ -166,6 +178,7 @@ int main()
                 case 3: ld_kernel<3><<<ctas, warps_per_cta * 32>>>(buf, out, window); break;
                 case 4: ld_kernel<4><<<ctas, warps_per_cta * 32>>>(buf, out, window); break;
                 case 5: ld_kernel<5><<<ctas, warps_per_cta * 32>>>(buf, out, window); break;
+                case 6: ld_kernel<6><<<ctas, warps_per_cta * 32>>>(buf, out, window); break;
             }
         };
         const float ms = time_ms(run);
@@ -175,6 +188,7 @@ int main()
                cyc / instr_per_sm, cyc / instr_per_sm / lines_per[mode],
                (mode == 4 ? 64.0 : 128.0) * lines_per[mode] * instr_per_sm / cyc);
     }
+    if (loads_only) return 0;
     {
         const float ms = time_ms([&]() { shfl_kernel<<<ctas, warps_per_cta * 32>>>(out); });
         const double instr_per_sm = (double)nwarps / sms * ITERS * 4;

@@ -69,6 +69,19 @@ def stage() -> int:
 # ------------------------------------------------------------------------------------------------
 # environment the reference expects, supplied from outside its files
 # ------------------------------------------------------------------------------------------------
+def swap_module_class():
+    """--module b200: the reference's transformer imports `MSDeformAttn` from models.ops.modules
+    (models/tce_deformable_transformer.py:20); hand it this repo's mirror of the class instead (same
+    constructor, state_dict keys and 3-tuple return), again without editing a reference file."""
+    pkg = importlib.import_module("tce-rvos_b200")
+    ref_modules = importlib.import_module("models.ops.modules")
+    ref_modules.MSDeformAttn = pkg.MSDeformAttn
+    importlib.import_module("models.ops.modules.ms_deform_attn").MSDeformAttn = pkg.MSDeformAttn
+    # `import models` has already run models/tce_deformable_transformer.py:20, which bound the name
+    importlib.import_module("models.tce_deformable_transformer").MSDeformAttn = pkg.MSDeformAttn
+    return pkg.MSDeformAttn
+
+
 def install_environment(op: str, cpu_stub: bool):
     import torch
 
@@ -218,6 +231,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--backbone", default=None)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--module", default="reference", choices=("reference", "b200"),
+                    help="which MSDeformAttn nn.Module class the reference transformer instantiates")
+    ap.add_argument("--fused", action="store_true",
+                    help="with --module b200: fused prologue (softmax + locations inside the gather kernel; encoder/FTF "
+                         "layers skip materialising them) and fused value epilogue")
+    ap.add_argument("--tf32", action="store_true",
+                    help="torch.backends.cuda.matmul.allow_tf32 = True (NOT the reference's setting; shows what bounds the "
+                         "model outside the hot path: its nn.Linear layers run as fp32 SIMT GEMMs by default)")
+    ap.add_argument("--profile", default=None, help="write a torch.profiler table of one extra step (top CUDA kernels) to this file")
     ap.add_argument("--compare", action="store_true",
                     help="after timing, run one more step on the OTHER operator in the same process (same weights, "
                          "same inputs) and report the largest relative difference of the model outputs")
@@ -237,6 +259,8 @@ def main():
     if world > 1:
         dist.init_process_group("gloo" if cpu else "nccl")
     ext_name = install_environment(a.op, cpu)
+    if a.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
 
     production = ["--with_box_refine", "--binary", "--freeze_text_encoder", "--f_token", "8", "--qtrans",
                   "--device", str(device)]
@@ -253,10 +277,25 @@ def main():
     flags = production + ["--backbone", backbone, "--enc_layers", str(layers), "--dec_layers", str(layers),
                           "--num_frames", str(T), "--batch_size", str(n_clips)]
     args = reference_args(flags)
+    module_cls = swap_module_class() if (a.module == "b200" and not cpu) else None
     torch.manual_seed(1234)
     from models import build_model
     model, criterion, _ = build_model(args)
     model.to(device)
+    n_fused = 0
+    if module_cls is not None:
+        for name, m in model.named_modules():
+            if isinstance(m, module_cls):
+                n_fused += 1
+                if a.fused:
+                    m.fused_prologue = True
+                    m.fused_value_epilogue = True
+                    m.check_shapes = "once"
+                    # only the decoder's cross attention consumes the returned locations / weights
+                    # (tce_deformable_transformer.py:752-758); encoder self-attention takes [0] (:543-544)
+                    # and the FTF layer binds but never reads them (:451-452)
+                    m.return_sampling = ".cross_attn" in name
+        assert n_fused > 0, "the reference transformer did not pick up the swapped module class"
     calls = count_op_calls()
     n_params = sum(p.numel() for p in model.parameters())
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
@@ -308,6 +347,8 @@ def main():
     sync()
     calls["fwd"] = calls["bwd"] = 0
     calls["events"] = {"fwd": [], "bwd": []}
+    b200_ext = None if (cpu or a.op != "b200") else importlib.import_module("tce-rvos_b200").load_extension()
+    launches0 = b200_ext.launch_count() if b200_ext else 0
     t0 = time.perf_counter()
     if not cpu:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -324,6 +365,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s = float(t)
     frames = T * n_clips * world * a.steps
+    b200_launches = (b200_ext.launch_count() - launches0) / a.steps if b200_ext else None
+    if a.profile and not cpu and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        with open(a.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
     compare = None
     if a.compare and not cpu and a.config == 3:
         fn = importlib.import_module("models.ops.functions.ms_deform_attn_func")
@@ -345,14 +394,14 @@ def main():
             compare[k] = float((x - y).abs().max() / y.abs().max())
     line = {
         "what": f"BASELINE.json configs[{a.config - 1}]: unmodified reference model on the {a.op} operator",
-        "op_extension": ext_name, "config": a.config, "backbone": backbone, "enc_dec_layers": layers,
+        "op_extension": ext_name, "module_class": a.module + ("+fused" if a.fused else ""), "config": a.config, "backbone": backbone, "enc_dec_layers": layers,
         "frames_per_clip": T, "clips_per_gpu": n_clips, "input": [H, W], "mode": "inference" if a.config == 3 else "train step (fwd+loss+bwd+clip+AdamW)",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dev_s / a.steps * 1e3,
         "frames_per_s": frames / dev_s, "op_calls_per_step": {k: calls[k] / a.steps for k in ("fwd", "bwd")},
         "op_ms_per_step": {k: sum(x.elapsed_time(y) for x, y in v) / a.steps for k, v in calls["events"].items()},
-        "params_M": n_params / 1e6, "trainable_params_M": n_train / 1e6,
+        "b200_kernel_launches_per_step": b200_launches, "params_M": n_params / 1e6, "trainable_params_M": n_train / 1e6,
         "result_checksum": float(r.float().abs().mean()) if hasattr(r, "float") else None,
-        "weights": "random init (seed 1234), synthetic clip", "dtype": "fp32", "compare_max_rel": compare,
+        "weights": "random init (seed 1234), synthetic clip", "dtype": "fp32" + (" (matmul TF32 allowed)" if a.tf32 else ""), "compare_max_rel": compare,
     }
     if rank == 0:
         print(json.dumps(line))
