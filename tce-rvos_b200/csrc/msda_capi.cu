@@ -176,13 +176,13 @@ int dispatch_fwd_generic(const Dims &d, int64_t group, const void *value, const 
 
 // ---- backward -----------------------------------------------------------------------------
 
-template <typename VT, bool PERMUTED = false>
+template <typename VT>
 int launch_cast(const float *scratch, void *grad_value, int64_t n, cudaStream_t st)
 {
     const int64_t n8 = n / 8;
     if (n8 > 0) {
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n8 + 255) / 256, 148 * 16));
-        msda::cast_scratch_kernel<VT, PERMUTED><<<grid, 256, 0, st>>>(scratch, static_cast<VT *>(grad_value), n8);
+        msda::cast_scratch_kernel<VT><<<grid, 256, 0, st>>>(scratch, static_cast<VT *>(grad_value), n8);
         ++g_launches;
         const int e = launch_status();
         if (e) return e;
@@ -200,7 +200,7 @@ int launch_bwd_fast(const Dims &d, const void *value, const int64_t *shapes, con
                     const void *loc, const void *aw, const void *go, GT *gv, void *gl, void *ga,
                     cudaStream_t st, const msda::ProArgs &pro = msda::ProArgs{})
 {
-    constexpr int HPW = 32 / msda::FastCfg<VT>::LPH;
+    constexpr int HPW = 32 / msda::BwdLanes<VT, GT>::LPH;
     const int64_t items = d.N * d.Lq * (d.M / HPW);
     if (items == 0) return MSDA_OK;
     constexpr int threads = 256;
@@ -277,7 +277,7 @@ int backward_impl(const msda_shape *shape, int64_t group, const void *value, con
                         ? launch_bwd_fast<__nv_bfloat16, float, float>(d, value, shapes, lsi, loc, aw, go, static_cast<float *>(ws), gl, ga, st)
                         : launch_bwd_fast<__nv_bfloat16, __nv_bfloat16, float>(d, value, shapes, lsi, loc, aw, go, static_cast<float *>(ws), gl, ga, st);
                 if (e) return e;
-                return launch_cast<__nv_bfloat16, true>(static_cast<const float *>(ws), gv, nval, st);
+                return launch_cast<__nv_bfloat16>(static_cast<const float *>(ws), gv, nval, st);
             }
             return (d.ldt == MSDA_F32)
                        ? launch_bwd_fast<__nv_bfloat16, float, __nv_bfloat16>(d, value, shapes, lsi, loc, aw, go, static_cast<__nv_bfloat16 *>(gv), gl, ga, st)

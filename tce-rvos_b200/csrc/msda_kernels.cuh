@@ -152,9 +152,9 @@ template <> struct FastCfg<__nv_bfloat16> {
 constexpr int kFastD = 32;
 constexpr int kFastLP = 16;
 
-// 16-byte load of CPL channels -> float[CPL]
-template <typename VT> struct VecIO;
-template <> struct VecIO<float> {
+// one vector load of CPL channels -> float[CPL] (16 bytes, or 8 bytes for 4 x bf16)
+template <typename VT, int CPL> struct VecIOn;
+template <> struct VecIOn<float, 4> {
     static __device__ __forceinline__ void load(const float *p, float (&v)[4])
     {
         const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
@@ -171,7 +171,7 @@ template <> struct VecIO<float> {
         __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
     }
 };
-template <> struct VecIO<__nv_bfloat16> {
+template <> struct VecIOn<__nv_bfloat16, 8> {
     static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8])
     {
         const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
@@ -205,6 +205,23 @@ template <> struct VecIO<__nv_bfloat16> {
         __stcs(reinterpret_cast<uint4 *>(p), t);
     }
 };
+
+// 4 x bf16 (8 bytes): the backward's 8-lanes-per-head layout for 16-bit values
+template <> struct VecIOn<__nv_bfloat16, 4> {
+    static __device__ __forceinline__ void unpack(const uint2 t, float (&v)[4])
+    {
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[4]) { unpack(__ldg(reinterpret_cast<const uint2 *>(p)), v); }
+    static __device__ __forceinline__ void zero(float (&v)[4]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+    static __device__ __forceinline__ void load_stream(const __nv_bfloat16 *p, float (&v)[4]) { unpack(__ldcs(reinterpret_cast<const uint2 *>(p)), v); }
+    static __device__ __forceinline__ void store_stream(__nv_bfloat16 *p, const float (&v)[4])
+    {
+        __stcs(reinterpret_cast<uint2 *>(p), make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3])));
+    }
+};
+template <typename VT> using VecIO = VecIOn<VT, FastCfg<VT>::CPL>;
 
 // Loads of the PPL points a lane owns: PPL*2 location scalars and PPL weights, contiguous.
 template <typename LT, int PPL> struct PointIO;
@@ -249,6 +266,27 @@ template <> struct PointIO<float, 4> {
     static __device__ __forceinline__ void store_aw(float *p, const float (&a)[4])
     {
         __stcs(reinterpret_cast<float4 *>(p), make_float4(a[0], a[1], a[2], a[3]));
+    }
+};
+template <> struct PointIO<__nv_bfloat16, 2> {
+    static __device__ __forceinline__ void load_loc(const __nv_bfloat16 *p, float (&xy)[4])
+    {
+        const uint2 t = __ldcs(reinterpret_cast<const uint2 *>(p));
+        xy[0] = __uint_as_float(t.x << 16); xy[1] = __uint_as_float(t.x & 0xffff0000u);
+        xy[2] = __uint_as_float(t.y << 16); xy[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void load_aw(const __nv_bfloat16 *p, float (&a)[2])
+    {
+        const uint32_t t = __ldcs(reinterpret_cast<const uint32_t *>(p));
+        a[0] = __uint_as_float(t << 16); a[1] = __uint_as_float(t & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void store_loc(__nv_bfloat16 *p, const float (&xy)[4])
+    {
+        __stcs(reinterpret_cast<uint2 *>(p), make_uint2(pack_bf16x2(xy[0], xy[1]), pack_bf16x2(xy[2], xy[3])));
+    }
+    static __device__ __forceinline__ void store_aw(__nv_bfloat16 *p, const float (&a)[2])
+    {
+        __stcs(reinterpret_cast<uint32_t *>(p), pack_bf16x2(a[0], a[1]));
     }
 };
 template <> struct PointIO<__nv_bfloat16, 4> {
@@ -579,27 +617,25 @@ __device__ __forceinline__ void red_add_v4_bf16x2_if(int pred, void *addr, uint3
                  :: "l"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(pred) : "memory");
 }
 
-template <typename VT, typename GT> struct GradScatter;
-template <> struct GradScatter<float, float> {
+// CPL = channels a lane holds.  16-bit values accumulate either in an fp32 scratch (GT = float; the
+// backward then uses the 8-lanes-per-head layout, CPL = 4, so that every reduction instruction
+// carries whole 128-byte lines like the fp32 kernel: with 4 lanes x 8 channels a line was two
+// 64-byte requests and the L2 sustained 20 % fewer line updates) or directly in 16 bits
+// (GT = VT, 4 lanes x 8 channels, one 64-byte bf16x2 request per line).
+template <typename VT, typename GT, int CPL> struct GradScatter;
+template <> struct GradScatter<float, float, 4> {
     static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[4])
     {
         red_add_v4_f32_if(pred, p, w * go[0], w * go[1], w * go[2], w * go[3]);
     }
 };
-// fp32 scratch for 16-bit values.  A lane holds 8 consecutive channels; written naively its two
-// 16-byte reductions would each cover HALF of a 32-byte sector, i.e. every sector of the line
-// would be hit by two separate L2 atomic requests.  The scratch therefore uses a permuted channel
-// order (channel 8j+4i+k of a head lives at float 16i+4j+k), so that reduction i of the 4 lanes
-// covers bytes [64i, 64i+64) of the line = two whole sectors, one request each.
-// cast_scratch_kernel undoes the permutation when it rounds to 16 bits.
-template <> struct GradScatter<__nv_bfloat16, float> {
-    static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[8])
+template <> struct GradScatter<__nv_bfloat16, float, 4> {
+    static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[4])
     {
         red_add_v4_f32_if(pred, p, w * go[0], w * go[1], w * go[2], w * go[3]);
-        red_add_v4_f32_if(pred, p + 64, w * go[4], w * go[5], w * go[6], w * go[7]);
     }
 };
-template <> struct GradScatter<__nv_bfloat16, __nv_bfloat16> {
+template <> struct GradScatter<__nv_bfloat16, __nv_bfloat16, 8> {
     static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[8])
     {
         red_add_v4_bf16x2_if(pred, p, pack_bf16x2(w * go[0], w * go[1]), pack_bf16x2(w * go[2], w * go[3]),
@@ -607,19 +643,23 @@ template <> struct GradScatter<__nv_bfloat16, __nv_bfloat16> {
     }
 };
 
+// lanes per head of the backward kernel for (value type, accumulation type)
+template <typename VT, typename GT> struct BwdLanes { static constexpr int LPH = FastCfg<VT>::LPH; };
+template <> struct BwdLanes<__nv_bfloat16, float> { static constexpr int LPH = 8; };
+
 // --------------------------------------------------------------------------------------------
 // FAST backward.
 // --------------------------------------------------------------------------------------------
 template <typename VT, typename LT, typename GT, bool PROLOGUE, bool TCE>
-__global__ void __launch_bounds__(256, (sizeof(VT) == 4 ? MSDA_BWD_MIN_BLOCKS_F32 : MSDA_BWD_MIN_BLOCKS_BF16))
+__global__ void __launch_bounds__(256, (BwdLanes<VT, GT>::LPH == 8 ? MSDA_BWD_MIN_BLOCKS_F32 : MSDA_BWD_MIN_BLOCKS_BF16))
 bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
                 const LT *__restrict__ aw, const VT *__restrict__ grad_out,
                 GT *__restrict__ grad_value, LT *__restrict__ grad_loc, LT *__restrict__ grad_aw,
                 int64_t n_items, int64_t Lq, int64_t S, int M, int log2P, ProArgs pro)
 {
-    using Cfg = FastCfg<VT>;
-    constexpr int CPL = Cfg::CPL, LPH = Cfg::LPH, HPW = kWarp / LPH, PPL = kFastLP / LPH;
+    constexpr int LPH = BwdLanes<VT, GT>::LPH, CPL = kFastD / LPH, HPW = kWarp / LPH, PPL = kFastLP / LPH;
+    using IO = VecIOn<VT, CPL>;
 
     const int lane = threadIdx.x & 31;
     const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -639,7 +679,7 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     PointIO<LT, PPL>::load_aw(aw + qh0 * kFastLP + lane * PPL, a);
 
     float go[CPL];
-    VecIO<VT>::load_stream(grad_out + (nq * M + m) * kFastD + j * CPL, go);
+    IO::load_stream(grad_out + (nq * M + m) * kFastD + j * CPL, go);
 
     int Hs[PPL], Ws[PPL], starts[PPL], lv[PPL];
 #pragma unroll
@@ -659,8 +699,7 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     const int gpixb = pix * static_cast<int>(sizeof(GT));
     const int64_t head_off = n * S * pix + m * kFastD;
     const char *vlane = reinterpret_cast<const char *>(value + head_off + j * CPL);
-    // fp32 scratch of a 16-bit value type is channel-permuted (see GradScatter): lane j starts at float 4j
-    char *glane = reinterpret_cast<char *>(grad_value + head_off + (sizeof(GT) != sizeof(VT) ? j * 4 : j * CPL));
+    char *glane = reinterpret_cast<char *>(grad_value + head_off + j * CPL);
     int rowW[4];
     if (TCE) {
 #pragma unroll
@@ -678,15 +717,15 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
         char *g0 = glane + static_cast<int64_t>(pv.base) * gpixb;
         char *g1 = g0 + static_cast<int64_t>(W) * gpixb;
         float v0[CPL], v1[CPL], v2[CPL], v3[CPL];
-        VecIO<VT>::zero(v0); VecIO<VT>::zero(v1); VecIO<VT>::zero(v2); VecIO<VT>::zero(v3);
-        if (pv.mask & 1) VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v0);
-        if (pv.mask & 2) VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v1);
-        if (pv.mask & 4) VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v2);
-        if (pv.mask & 8) VecIO<VT>::load(reinterpret_cast<const VT *>(r1 + pixb), v3);
-        GradScatter<VT, GT>::add(pv.mask & 1, g0, pv.w0, go);
-        GradScatter<VT, GT>::add(pv.mask & 2, g0 + gpixb, pv.w1, go);
-        GradScatter<VT, GT>::add(pv.mask & 4, g1, pv.w2, go);
-        GradScatter<VT, GT>::add(pv.mask & 8, g1 + gpixb, pv.w3, go);
+        IO::zero(v0); IO::zero(v1); IO::zero(v2); IO::zero(v3);
+        if (pv.mask & 1) IO::load(reinterpret_cast<const VT *>(r0), v0);
+        if (pv.mask & 2) IO::load(reinterpret_cast<const VT *>(r0 + pixb), v1);
+        if (pv.mask & 4) IO::load(reinterpret_cast<const VT *>(r1), v2);
+        if (pv.mask & 8) IO::load(reinterpret_cast<const VT *>(r1 + pixb), v3);
+        GradScatter<VT, GT, CPL>::add(pv.mask & 1, g0, pv.w0, go);
+        GradScatter<VT, GT, CPL>::add(pv.mask & 2, g0 + gpixb, pv.w1, go);
+        GradScatter<VT, GT, CPL>::add(pv.mask & 4, g1, pv.w2, go);
+        GradScatter<VT, GT, CPL>::add(pv.mask & 8, g1 + gpixb, pv.w3, go);
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
@@ -754,19 +793,15 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 // --------------------------------------------------------------------------------------------
 // 16-bit grad_value epilogue: round the fp32 scratch once.
 // --------------------------------------------------------------------------------------------
-template <typename VT, bool PERMUTED>
+template <typename VT>
 __global__ void __launch_bounds__(256)
 cast_scratch_kernel(const float *__restrict__ src, VT *__restrict__ dst, int64_t n_vec8)
 {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec8; i += stride) {
-        // PERMUTED (fast-path scratch, 32-channel heads): output channels 8j..8j+7 of a head come from
-        // scratch floats [4j, 4j+4) and [16+4j, 16+4j+4) of that head's 32-float row.
-        const int64_t row = i >> 2;
-        const int j = static_cast<int>(i & 3);
         const float4 *s4 = reinterpret_cast<const float4 *>(src);
-        const float4 a = __ldcs(PERMUTED ? s4 + row * 8 + j : s4 + 2 * i);
-        const float4 b = __ldcs(PERMUTED ? s4 + row * 8 + 4 + j : s4 + 2 * i + 1);
+        const float4 a = __ldcs(s4 + 2 * i);
+        const float4 b = __ldcs(s4 + 2 * i + 1);
         const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         VT o[8];
 #pragma unroll

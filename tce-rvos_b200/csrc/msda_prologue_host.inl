@@ -72,7 +72,7 @@ int msda_prologue_backward(const msda_shape *shape, const void *value, const int
                 ? launch_bwd_fast<__nv_bfloat16, float, float, true>(d, value, shapes, lsi, offsets, logits, go, static_cast<float *>(ws), g_off, g_logit, st, pro)
                 : launch_bwd_fast<__nv_bfloat16, __nv_bfloat16, float, true>(d, value, shapes, lsi, offsets, logits, go, static_cast<float *>(ws), g_off, g_logit, st, pro);
         if (e) return e;
-        return launch_cast<__nv_bfloat16, true>(static_cast<const float *>(ws), gv, nval, st);
+        return launch_cast<__nv_bfloat16>(static_cast<const float *>(ws), gv, nval, st);
     }
     return (d.ldt == MSDA_F32)
                ? launch_bwd_fast<__nv_bfloat16, float, __nv_bfloat16, true>(d, value, shapes, lsi, offsets, logits, go, static_cast<__nv_bfloat16 *>(gv), g_off, g_logit, st, pro)

@@ -172,7 +172,11 @@ def test_config2_bf16_against_fp64_oracle(capi, oracle, loc_dtype):
     # direct 16-bit vector atomics (no fp32 scratch): one rounding per contribution -> looser
     gv2, gl2, ga2 = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"], use_workspace=False)
     assert oracle.max_rel(gv2.float().cpu(), rv) < 1.5e-1
-    assert torch.equal(gl2, got[1]) and torch.equal(ga2, got[2])
+    # the two paths use different lane layouts (8 lanes x 4 channels with the fp32 scratch, 4 lanes x 8 channels
+    # without), so the channel dot products are summed in a different order
+    tol = 1e-5 if loc_dtype == torch.float32 else BF16_TOL
+    assert oracle.max_rel(gl2.float().cpu(), got[1].float().cpu()) < tol
+    assert oracle.max_rel(ga2.float().cpu(), got[2].float().cpu()) < tol
 
 
 def test_decoder_and_ftf_shapes(capi, oracle):
