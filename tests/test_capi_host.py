@@ -150,3 +150,29 @@ def test_drop_in_under_the_reference_module_name(pkg):
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         theirs(torch.zeros(1, 1, 256), torch.zeros(1, 1, 4, 2), torch.zeros(1, 4, 256),
                torch.tensor([[1, 1]] * 4), torch.tensor([0, 1, 2, 3]))
+
+
+def test_aux_entry_points_validate_before_touching_cuda(capi):
+    """msda_value_epilogue / msda_topk_samples (rows f2, f3) reject bad arguments without a GPU."""
+    lib = capi.load()
+    F32, BF16, F64 = capi.MSDA_F32, capi.MSDA_BF16, capi.MSDA_F64
+    assert lib.msda_value_epilogue(0, 256, None, F32, None, None, F32, None) == 0              # nothing to do
+    assert lib.msda_value_epilogue(4, 256, None, F32, None, None, F32, None) == capi.MSDA_E_NULL
+    assert lib.msda_value_epilogue(-1, 256, None, F32, None, None, F32, None) == capi.MSDA_E_SHAPE
+    buf = (C.c_char * 4096)()
+    addr = (C.addressof(buf) + 15) & ~15                                                        # 16-byte aligned host address
+    assert lib.msda_value_epilogue(2, 12, addr, F32, None, addr, F32, None) == capi.MSDA_E_UNSUPPORTED   # width % 8
+    assert lib.msda_value_epilogue(2, 16, addr + 4, F32, None, addr, F32, None) == capi.MSDA_E_ALIGN
+    assert lib.msda_value_epilogue(2, 16, addr, F64, None, addr, F32, None) == capi.MSDA_E_DTYPE
+
+    sh = capi.make_shape(2, 1, 5, 8, 1, 4, 4, F32, F32)
+    assert lib.msda_topk_samples(C.byref(sh), 30, None, None, None, None, None, None, None) == capi.MSDA_E_NULL
+    assert lib.msda_topk_samples(C.byref(sh), 0, addr, addr, None, addr, addr, None, None) == capi.MSDA_E_UNSUPPORTED
+    assert lib.msda_topk_samples(C.byref(sh), 129, addr, addr, None, addr, addr, None, None) == capi.MSDA_E_UNSUPPORTED
+    big = capi.make_shape(2, 1, 5, 8, 1, 4, 32, F32, F32)                                       # 1024 candidates
+    assert lib.msda_topk_samples(C.byref(big), 30, addr, addr, None, addr, addr, None, None) == capi.MSDA_E_UNSUPPORTED
+    empty = capi.make_shape(0, 1, 5, 8, 1, 4, 4, F32, F32)
+    assert lib.msda_topk_samples(C.byref(empty), 30, None, None, None, None, None, None, None) == 0
+    half = capi.make_shape(2, 1, 5, 8, 1, 4, 4, F32, capi.MSDA_F16)
+    assert lib.msda_topk_samples(C.byref(half), 30, addr, addr, None, addr, addr, None, None) == capi.MSDA_E_DTYPE
+    assert lib.msda_topk_samples(None, 30, addr, addr, None, addr, addr, None, None) == capi.MSDA_E_NULL

@@ -615,3 +615,39 @@ def test_decoder_sample_topk_ties_and_bf16(capi, oracle):
     ref_s = torch.gather((lb.float() / vb.float()[:, None, None, :, None, :]).bfloat16().view(N, Lq, -1, 2), 2,
                          ri.unsqueeze(-1).repeat(1, 1, 1, 2))
     assert torch.equal(s.cpu(), ref_s)
+
+
+# ------------------------------------------------------------------------------------------------
+# randomised shapes: fast and generic kernels, ragged levels, single rows/columns, Lq = 1
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shapes_against_the_c_oracle(capi, oracle, seed):
+    """Seeded random problem shapes (heads, channels, levels x points, level sizes down to 1x1, 1..7 frames,
+    1..97 queries, locations up to 20 % outside the map) through the C ABI in fp32, against the fp64 C
+    restatement of the reference kernels' arithmetic (oracle/msda_oracle.c) on the same fp32-rounded inputs."""
+    rng = np.random.default_rng(1000 + seed)
+    fast = seed % 2 == 0                       # D = 32 and L*P = 16 -> the fast kernels, else the generic ones
+    if fast:
+        M, D = int(rng.choice([4, 8, 12, 16])), 32
+        L, P = [(4, 4), (2, 8), (1, 16), (8, 2), (16, 1)][int(rng.integers(0, 5))]
+    else:
+        M, D = int(rng.integers(1, 7)), int(rng.choice([1, 3, 8, 16, 33, 48, 64]))
+        L, P = int(rng.integers(1, 6)), int(rng.integers(1, 6))
+    levels = [(int(rng.integers(1, 14)), int(rng.integers(1, 14))) for _ in range(L)]
+    N, Lq = int(rng.integers(1, 8)), int(rng.integers(1, 98))
+    S = sum(h * w for h, w in levels)
+    g = torch.Generator().manual_seed(seed)
+    value = torch.randn(N, S, M, D, generator=g)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.4 - 0.2
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    go = torch.randn(N, Lq, M * D, generator=g)
+    shapes, lsi = oracle.level_tensors(levels)
+    lib = capi.load()
+    sh = capi.make_shape(N, S, Lq, M, D, L, P, capi.MSDA_F32, capi.MSDA_F32)
+    assert lib.msda_kernel_name(C.byref(sh), 0).startswith(b"fwd_fast" if fast else b"fwd_generic")
+    out = capi.forward(value.to(DEV), shapes.to(DEV), lsi.to(DEV), loc.to(DEV), aw.to(DEV))
+    gv, gl, ga = capi.backward(value.to(DEV), shapes.to(DEV), lsi.to(DEV), loc.to(DEV), aw.to(DEV), go.to(DEV))
+    ref_out = torch.as_tensor(oracle.c_forward(value.double(), shapes, lsi, loc.double(), aw.double()))
+    rv, rl, ra = (torch.as_tensor(x) for x in oracle.c_backward(value.double(), shapes, lsi, loc.double(), aw.double(), go.double()))
+    assert oracle.max_rel(out.cpu(), ref_out.view_as(out.cpu())) < FWD_TOL
+    check_grads(oracle, (gv, gl, ga), (rv, rl, ra), loc, levels, GRAD_TOL, stress=True)
