@@ -130,8 +130,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def cpu_step_inputs(frames, lq=None, seed=0):
     import torch
-    from oracle import msda_oracle as O
-    inp = O.make_inputs("model", frames, LEVELS_A, M=M, D=D, P=P, seed=seed, dtype=torch.float32)
+    from tools import synthetic
+    inp = synthetic.make_inputs("model", frames, LEVELS_A, M=M, D=D, P=P, seed=seed, dtype=torch.float32)
     if lq is not None and lq < inp["loc"].shape[1]:
         # a bounded sample: the first lq queries of every frame (value keeps its full size)
         for k in ("loc", "aw", "grad_out"):
@@ -246,12 +246,12 @@ def run_ours(args, rank, local_rank, world):
     pkg = importlib.import_module("tce-rvos_b200")
     capi = importlib.import_module("tce-rvos_b200.capi")
     ext = pkg.load_extension()
-    from oracle import msda_oracle as O            # input generator only (the checker is not timed here)
+    from tools import synthetic                    # seeded workload generator; the oracle is not imported on this arm
 
     tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
     sets = []
     for i in range(N_INPUT_SETS):
-        inp = O.make_inputs("model", FRAMES_PER_GPU, LEVELS_A, M=M, D=D, P=P, seed=100 * rank + i, dtype=torch.float32)
+        inp = synthetic.make_inputs("model", FRAMES_PER_GPU, LEVELS_A, M=M, D=D, P=P, seed=100 * rank + i, dtype=torch.float32)
         sets.append(dict(value=inp["value"].to(dev, tdt).requires_grad_(True), loc=inp["loc"].to(dev).requires_grad_(True),
                          aw=inp["aw"].to(dev).requires_grad_(True), go=inp["grad_out"].to(dev, tdt)))
     shapes, lsi = inp["shapes"].to(dev), inp["lsi"].to(dev)

@@ -4,7 +4,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 capi = importlib.import_module("tce-rvos_b200.capi")
-from oracle import msda_oracle as O
+from tools import synthetic as O
 
 nbytes = 173_000_000
 h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()

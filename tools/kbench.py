@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("tce-rvos_b200")
 capi = importlib.import_module("tce-rvos_b200.capi")
-from oracle import msda_oracle as O  # noqa: E402  (input generator only)
+from tools import synthetic as O  # noqa: E402  (seeded workload generator)
 
 
 def main():
