@@ -17,10 +17,16 @@ capi = importlib.import_module("tce-rvos_b200.capi")
 
 def timed(f, reps=20, warm=3, per_graph=8):
     """Median time of one call.  The calls are replayed from a CUDA graph holding `per_graph` of them so
-    that the GPU, not the Python launch path, is what is timed (these kernels run for 10-50 us)."""
+    that the GPU, not the Python launch path, is what is timed (these kernels run for 10-50 us).
+    AUXBENCH_NO_GRAPH=1 (ncu captures): plain launches, 2 calls."""
     for i in range(warm):
         f(i)
     torch.cuda.synchronize()
+    if os.environ.get("AUXBENCH_NO_GRAPH"):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); f(0); f(1); b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / 2
     side = torch.cuda.Stream()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.stream(side):

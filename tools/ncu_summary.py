@@ -45,7 +45,10 @@ KEYS = [
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):                      # a raw page exported on the GPU box (tools/final_validation.sh)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     return rows[0], rows[1], rows[2:]
 
@@ -75,7 +78,7 @@ def main():
             f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (per-launch times are cold-cache and "
                     "serialised: compare SHARES).  Only the launches of the device-timed loop (3 warm-up + 20 steps, 2 kernels per step; the "
                     "grad_value zero-fill is a cudaMemsetAsync, not a kernel) are listed; the e2e leg that follows launches the "
-                    "same two kernels on 8 frame chunks per step.  Full list: `" + f"{tag}_launches.csv`.\n\n")
+                    "same two kernels once per frame (10 chunks per step).  Full list: `" + f"{tag}_launches.csv`.\n\n")
             f.write("| kernel | launches | mean us | share of captured GPU time |\n|---|---|---|---|\n")
             for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
                 f.write(f"| `{k[:110]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {100 * sum(v) / total:.1f}% |\n")
