@@ -155,6 +155,18 @@ def test_config2_fp32_against_fp64_oracle(capi, oracle, kind):
     check_grads(oracle, got, (rv, rl, ra), inp["loc"], levels, GRAD_TOL)
 
 
+def test_baseline_config0_forward_on_gpu(pkg, oracle):
+    """BASELINE.json configs[0] (5 frames, level set A, fp32 forward) through the reference-facing
+    MSDeformAttnFunction: equal to the reference's CPU path within the fp32 forward tolerance."""
+    inp = oracle.make_inputs("model", 5, oracle.LEVELS_A, seed=0)
+    t = dev_inputs(inp, torch.float32)
+    out = pkg.MSDeformAttnFunction.apply(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], 64)
+    ref64 = oracle.core_pytorch(inp["value"].double(), inp["shapes"], inp["loc"].double(), inp["aw"].double())
+    assert oracle.max_rel(out.cpu(), ref64) < FWD_TOL
+    ref32 = oracle.core_pytorch(inp["value"], inp["shapes"], inp["loc"], inp["aw"])      # what the reference returns on CPU
+    assert torch.allclose(out.cpu(), ref32, rtol=1e-4, atol=1e-5)
+
+
 @pytest.mark.parametrize("loc_dtype", [torch.float32, torch.bfloat16])
 def test_config2_bf16_against_fp64_oracle(capi, oracle, loc_dtype):
     levels = oracle.LEVELS_A

@@ -167,3 +167,16 @@ def test_value_epilogue_restatement(oracle):
     assert torch.equal(out[m], torch.zeros_like(out[m])) and torch.equal(out[~m], v[~m])
     assert oracle.value_epilogue(v, m, torch.bfloat16).dtype == torch.bfloat16
     assert torch.equal(oracle.value_epilogue(v), v)
+
+
+def test_baseline_config0_cpu_forward(oracle):
+    """BASELINE.json configs[0], the reference's own CPU-runnable case: standalone forward through
+    ms_deform_attn_core_pytorch, B*T = 5 frames, levels 45x80 / 23x40 / 12x20 / 6x10, 8 heads x 32 ch,
+    4 points, fp32 synthetic tensors.  The PyTorch restatement in fp32 agrees with the fp64 C restatement
+    of the CUDA kernels' arithmetic to fp32 rounding (1e-6)."""
+    inp = oracle.make_inputs("model", 5, oracle.LEVELS_A, seed=0)
+    out32 = oracle.core_pytorch(inp["value"], inp["shapes"], inp["loc"], inp["aw"])
+    assert out32.shape == (5, 4820, 256) and out32.dtype == torch.float32
+    ref = torch.as_tensor(oracle.c_forward(inp["value"].double(), inp["shapes"], inp["lsi"], inp["loc"].double(),
+                                           inp["aw"].double())).view_as(out32)
+    assert oracle.max_rel(out32, ref) < 1e-5
