@@ -176,3 +176,27 @@ def test_aux_entry_points_validate_before_touching_cuda(capi):
     half = capi.make_shape(2, 1, 5, 8, 1, 4, 4, F32, capi.MSDA_F16)
     assert lib.msda_topk_samples(C.byref(half), 30, addr, addr, None, addr, addr, None, None) == capi.MSDA_E_DTYPE
     assert lib.msda_topk_samples(None, 30, addr, addr, None, addr, addr, None, None) == capi.MSDA_E_NULL
+
+
+def test_header_is_plain_c_and_links(tmp_path, capi):
+    """include/msda_b200.h is the drop-in boundary: it must compile as C99 (no C++ or torch types) and a
+    plain C program must link against libmsda_b200.so and call it (introspection only: no GPU here)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "msda_b200.h"\n'
+        "int main(void) {\n"
+        "  msda_shape s = {10, 4820, 4820, 8, 32, 4, 4, MSDA_F32, MSDA_F32};\n"
+        '  printf("%d %s %lld %d\\n", msda_abi_version(), msda_kernel_name(&s, 1),\n'
+        "         (long long)msda_algorithmic_bytes(&s, 2), msda_forward(&s, 0, 0, 0, 0, 0, 0, 0));\n"
+        "  return 0;\n}\n")
+    exe = tmp_path / "use_abi"
+    lib = capi.library_path()
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+                    f"-L{lib.parent}", "-lmsda_b200", f"-Wl,-rpath,{lib.parent}", "-Wl,-rpath,/usr/local/cuda/lib64"],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["1", "bwd_fast_d32_f32", str(4 * 10 * (768 * 4820 + 1664 * 4820)), str(capi.MSDA_E_NULL)]
