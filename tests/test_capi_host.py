@@ -200,3 +200,29 @@ def test_header_is_plain_c_and_links(tmp_path, capi):
                    check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert out == ["1", "bwd_fast_d32_f32", str(4 * 10 * (768 * 4820 + 1664 * 4820)), str(capi.MSDA_E_NULL)]
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not present on this machine")
+def test_package_replaces_the_models_ops_directory(tmp_path):
+    """The package mirrors the layout of the reference's models/ops (functions/, modules/), so the directory
+    can be replaced wholesale: with models/ops pointing at tce-rvos_b200 the UNMODIFIED
+    models/tce_deformable_transformer.py imports this repo's MSDeformAttn and builds its layers with it."""
+    import os
+    import subprocess
+    (tmp_path / "models").mkdir()
+    for p in (REF / "models").iterdir():
+        if p.name != "ops":
+            os.symlink(p, tmp_path / "models" / p.name)
+    os.symlink(ROOT / "tce-rvos_b200", tmp_path / "models" / "ops")
+    os.symlink(REF / "util", tmp_path / "util")
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, '.')\n"
+        "import models.tce_deformable_transformer as T\n"
+        "from models.ops.modules import MSDeformAttn\n"
+        "from models.ops.functions import MSDeformAttnFunction\n"
+        "layer = T.DeformableTransformerEncoderLayer(256, 1024, 0.1, 'relu', 4, 8, 4)\n"
+        "assert type(layer.self_attn) is MSDeformAttn and hasattr(layer.self_attn, 'fused_prologue')\n"
+        "print('ok', MSDeformAttn.__module__)\n" % str(ROOT / "tools" / "shims"))
+    res = subprocess.run([sys.executable, "-c", code], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.split()[-2:] == ["ok", "models.ops.modules.ms_deform_attn"]
