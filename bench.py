@@ -208,6 +208,28 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def count_line_updates(loc, levels):
+    """Number of 128-byte grad_value line updates one backward issues: one per (query, head, point, corner)
+    whose corner lies inside its level (the reference's gating, ms_deform_im2col_cuda.cuh:441 and :57-79)."""
+    import torch
+    total = 0
+    for l, (H, W) in enumerate(levels):
+        x = loc[:, :, :, l, :, 0] * W - 0.5
+        y = loc[:, :, :, l, :, 1] * H - 0.5
+        inside = (x > -1) & (y > -1) & (x < W) & (y < H)
+        x0, y0 = torch.floor(x), torch.floor(y)
+        for dy in (0, 1):
+            for dx in (0, 1):
+                ok = inside & (x0 + dx >= 0) & (x0 + dx <= W - 1) & (y0 + dy >= 0) & (y0 + dy <= H - 1)
+                total += int(ok.sum())
+    return total
+
+
+# measured on this pool (profiles/r01_microbench_bulk_red.txt, r01_microbench_l1_shapes.txt): the chip sustains
+# 47.5-49.4 G updates/s of 128-byte lines through red.global.add.v4.f32 (or TMA bulk reductions) = ~6.1 TB/s
+L2_REDUCTION_PEAK_GLINES = 47.5
+
+
 def bind_to_gpu_numa_node(index):
     """The e2e leg moves 173 MB each way per step through pinned host memory.  torchrun does not bind
     ranks to the socket their GPU hangs off, so with several ranks the copies cross the inter-socket
@@ -256,6 +278,7 @@ def run_ours(args, rank, local_rank, world):
                          aw=inp["aw"].to(dev).requires_grad_(True), go=inp["grad_out"].to(dev, tdt)))
     shapes, lsi = inp["shapes"].to(dev), inp["lsi"].to(dev)
     host_set = inp                                                  # last set, for the e2e leg
+    line_updates = count_line_updates(sets[0]["loc"].detach(), LEVELS_A)   # what bounds the backward
     N, S, Lq = FRAMES_PER_GPU, inp["value"].shape[1], inp["loc"].shape[1]
     qh_per_step = N * Lq * M
     fn = pkg.MSDeformAttnFunction.apply
@@ -375,6 +398,13 @@ def run_ours(args, rank, local_rank, world):
                            "fwd+bwd": {"us": ms_total * 1e3 / args.steps,
                                        "GB/s": (bytes_fwd + bytes_bwd) / (ms_total * 1e3 / args.steps) / 1e3,
                                        "frac": (bytes_fwd + bytes_bwd) / (ms_total * 1e3 / args.steps) / 1e3 / peak}}}
+    # the bound that actually limits the backward: L2 reduction throughput (informative, next to the HBM figure)
+    roofline["l2_reduction"] = {
+        "what": "backward pass: 128-byte grad_value line updates (red.global.add.v4.f32) per second against the rate the "
+                "L2 sustains in a microbenchmark on this pool (profiles/r01_microbench_bulk_red.txt)",
+        "line_updates_per_launch": line_updates, "achieved_Glines_s": line_updates / (b_us * 1e-6) / 1e9,
+        "peak_Glines_s": L2_REDUCTION_PEAK_GLINES, "frac": line_updates / (b_us * 1e-6) / 1e9 / L2_REDUCTION_PEAK_GLINES,
+        "payload_TB_s": line_updates * 128 / (b_us * 1e-6) / 1e12}
     traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(traffic_path):
         try:
