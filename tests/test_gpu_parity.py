@@ -663,3 +663,29 @@ def test_random_shapes_against_the_c_oracle(capi, oracle, seed):
     rv, rl, ra = (torch.as_tensor(x) for x in oracle.c_backward(value.double(), shapes, lsi, loc.double(), aw.double(), go.double()))
     assert oracle.max_rel(out.cpu(), ref_out.view_as(out.cpu())) < FWD_TOL
     check_grads(oracle, (gv, gl, ga), (rv, rl, ra), loc, levels, GRAD_TOL, stress=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# fp16 (generic kernels) and 16-bit values at non-TCE geometry
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("vdt,ldt", [(torch.float16, torch.float32), (torch.float16, torch.float16),
+                                     (torch.bfloat16, torch.float32)])
+def test_sixteen_bit_generic_kernels(capi, oracle, vdt, ldt):
+    """Half-precision values take the generic kernels (fp32 accumulation, fp32 scratch for grad_value):
+    TCE head geometry in fp16, and a 48-channel geometry in bf16 that the fast kernels do not cover."""
+    D = 32 if vdt == torch.float16 else 48
+    levels = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    inp = oracle.make_inputs("model", 2, levels, M=4, D=D, P=4, seed=31)
+    t = dev_inputs(inp, vdt, ldt)
+    lib = capi.load()
+    sh = capi.shape_of(t["value"], t["loc"], 4)
+    assert lib.msda_kernel_name(C.byref(sh), 0) == b"fwd_generic"
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    gv, gl, ga = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(t["value"].cpu().double(), inp["shapes"], t["loc"].cpu().double(),
+                                                      t["aw"].cpu().double(), t["grad_out"].cpu().double())
+    tol = 2e-3 if vdt == torch.float16 else BF16_TOL          # fp16: 11-bit mantissa outputs
+    assert oracle.max_rel(out.float().cpu(), ref_out) < tol
+    eps = 1e-4 if ldt == torch.float32 else 5e-3
+    check_grads(oracle, (gv.float(), gl.float(), ga.float()), (rv, rl, ra), t["loc"].float().cpu(), levels, tol if ldt == torch.float32 else 1e-2,
+                eps_px=eps, stress=True)
