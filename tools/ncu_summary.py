@@ -102,6 +102,24 @@ def main():
                 for k in KEYS:
                     if k in idx and r[idx[k]] != "":
                         f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
+                # derived: sectors per request (north_star asks for it), achieved DRAM GB/s
+                def num(k):
+                    try:
+                        return float(r[idx[k]].replace(",", ""))
+                    except Exception:
+                        return None
+                for op in ("ld", "red"):
+                    rq, sc = num(f"l1tex__t_requests_pipe_lsu_mem_global_op_{op}.sum"), num(f"l1tex__t_sectors_pipe_lsu_mem_global_op_{op}.sum")
+                    if rq and sc:
+                        f.write(f"| derived: sectors per request, global {op} | {sc / rq:.2f} | sector/request |\n")
+                try:
+                    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
+                    b = num("dram__bytes_read.sum") * scale[units[idx["dram__bytes_read.sum"]]] + \
+                        num("dram__bytes_write.sum") * scale[units[idx["dram__bytes_write.sum"]]]
+                    t_us = num("gpu__time_duration.sum") * {"us": 1, "ms": 1e3, "ns": 1e-3}[units[idx["gpu__time_duration.sum"]]]
+                    f.write(f"| derived: achieved DRAM throughput | {b / t_us / 1e3:.0f} | GB/s |\n")
+                except Exception:
+                    pass
                 f.write("\n")
                 try:
                     b = float(r[idx["dram__bytes_read.sum"]]) + float(r[idx["dram__bytes_write.sum"]])
