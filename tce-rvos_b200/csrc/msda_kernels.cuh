@@ -75,8 +75,11 @@ __device__ __forceinline__ PointGeom<A> resolve_point(A x, A y, int H, int W)
                         (h_im < static_cast<A>(H)) && (w_im < static_cast<A>(W));
     const A hf = floor_acc(h_im);
     const A wf = floor_acc(w_im);
-    g.lh = h_im - hf;
-    g.lw = w_im - wf;
+    // A gated-off point must contribute exactly nothing, also when the location is non-finite or
+    // overflows (inf - inf = NaN would otherwise reach the fast kernels' fmaf(w, 0, acc)); the
+    // reference skips such points entirely (ms_deform_im2col_cuda.cuh:441).
+    g.lh = inside ? h_im - hf : static_cast<A>(0);
+    g.lw = inside ? w_im - wf : static_cast<A>(0);
     // Only converted when inside (finite, in range); otherwise the value is never used.
     g.h_low = inside ? static_cast<int>(hf) : 0;
     g.w_low = inside ? static_cast<int>(wf) : 0;
@@ -718,14 +721,37 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
         char *g1 = g0 + static_cast<int64_t>(W) * gpixb;
         float v0[CPL], v1[CPL], v2[CPL], v3[CPL];
         IO::zero(v0); IO::zero(v1); IO::zero(v2); IO::zero(v3);
-        if (pv.mask & 1) IO::load(reinterpret_cast<const VT *>(r0), v0);
-        if (pv.mask & 2) IO::load(reinterpret_cast<const VT *>(r0 + pixb), v1);
-        if (pv.mask & 4) IO::load(reinterpret_cast<const VT *>(r1), v2);
-        if (pv.mask & 8) IO::load(reinterpret_cast<const VT *>(r1 + pixb), v3);
-        GradScatter<VT, GT, CPL>::add(pv.mask & 1, g0, pv.w0, go);
-        GradScatter<VT, GT, CPL>::add(pv.mask & 2, g0 + gpixb, pv.w1, go);
-        GradScatter<VT, GT, CPL>::add(pv.mask & 4, g1, pv.w2, go);
-        GradScatter<VT, GT, CPL>::add(pv.mask & 8, g1 + gpixb, pv.w3, go);
+        // MSDA_EXP 10..13: timing experiments that isolate the two halves of the backward
+        // (profiles/r02_bwd_split.md); never product.
+#if MSDA_EXP == 12
+        constexpr bool kLoads = false;
+#elif MSDA_EXP == 13
+        constexpr bool kLoads = p < 8;
+#else
+        constexpr bool kLoads = true;
+#endif
+#if MSDA_EXP == 10
+        constexpr bool kReds = false;
+#elif MSDA_EXP == 11 || MSDA_EXP == 13
+        constexpr bool kReds = p < 8;
+#else
+        constexpr bool kReds = true;
+#endif
+        if (kLoads) {
+            if (pv.mask & 1) IO::load(reinterpret_cast<const VT *>(r0), v0);
+            if (pv.mask & 2) IO::load(reinterpret_cast<const VT *>(r0 + pixb), v1);
+            if (pv.mask & 4) IO::load(reinterpret_cast<const VT *>(r1), v2);
+            if (pv.mask & 8) IO::load(reinterpret_cast<const VT *>(r1 + pixb), v3);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) { v0[c] = pv.w0; v1[c] = pv.w1; v2[c] = pv.w2; v3[c] = pv.w3; }
+        }
+        if (kReds) {
+            GradScatter<VT, GT, CPL>::add(pv.mask & 1, g0, pv.w0, go);
+            GradScatter<VT, GT, CPL>::add(pv.mask & 2, g0 + gpixb, pv.w1, go);
+            GradScatter<VT, GT, CPL>::add(pv.mask & 4, g1, pv.w2, go);
+            GradScatter<VT, GT, CPL>::add(pv.mask & 8, g1 + gpixb, pv.w3, go);
+        }
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
