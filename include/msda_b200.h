@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MSDA_ABI_VERSION 2
+#define MSDA_ABI_VERSION 1
 
 /* element types */
 enum {
@@ -100,13 +100,6 @@ int         msda_check_im2col_step(int64_t n_frames, int im2col_step);
  * gpu_launches claim). */
 int64_t     msda_launch_count(void);
 
-/* Kernel-family selection for the encoder-sized calls (process-wide; initial value from the environment
- * variable MSDA_TILE, default -1): -1 = by size (persistent SM-resident kernels when every SM gets a few
- * hundred queries and a workspace is supplied, one-shot kernels otherwise), 0 = always one-shot,
- * 1 = persistent wherever applicable (tests cover them at small sizes this way).  Any other argument only
- * queries.  Returns the previous mode.  Results agree between the families to rounding. */
-int         msda_tile_mode(int mode);
-
 /* ---- device-pointer operators --------------------------------------------------- */
 
 /* out[n,q,m,:] = sum_{l,p} attn_weight * bilinear(value_l[n,:,m,:], loc)   (a3-a5) */
@@ -118,22 +111,6 @@ int msda_forward(const msda_shape *shape,
                  const void *attn_weight,
                  void *out,
                  void *stream);
-
-/* msda_forward with a workspace: encoder-sized calls at the TCE geometry run on a persistent kernel that
- * schedules itself through a few grab counters in device memory (msda_forward_workspace_bytes(), 0 when
- * the shape does not use it).  The workspace is scratch: no initialisation needed, contents undefined
- * afterwards, must not be shared by calls running concurrently.  workspace == NULL is always legal and
- * selects the one-shot kernels (same results). */
-size_t msda_forward_workspace_bytes(const msda_shape *shape);
-int msda_forward_ws(const msda_shape *shape,
-                    const void *value,
-                    const int64_t *spatial_shapes,
-                    const int64_t *level_start_index,
-                    const void *sampling_loc,
-                    const void *attn_weight,
-                    void *out,
-                    void *workspace, size_t workspace_bytes,
-                    void *stream);
 
 /* Bytes of scratch msda_backward wants for this shape (0 when none is needed: fp32/fp64
  * accumulate in place; bf16/f16 grad_value is accumulated in fp32 scratch and rounded once). */

@@ -27,6 +27,9 @@ INCLUDE = PKG_DIR.parent / "include"
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo"]   # no --use_fast_math: IEEE division / expf
+# The shared CUDA runtime: one cudart in the process next to torch's (which is loaded first and has the same
+# soname), and no copy of the whole runtime's symbol table inside the shipped library.
+LINK_FLAGS = ["--cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 
 CAPI_SOURCES = ["msda_capi.cu"]
 CAPI_DEPS = ["msda_kernels.cuh", "msda_prologue_host.inl", "msda_host_pipeline.inl", "msda_aux_kernels.cuh", "msda_aux_host.inl"]
@@ -59,6 +62,11 @@ def _write_stamp(target: Path, stamp_value: str) -> None:
     target.with_suffix(target.suffix + ".stamp").write_text(stamp_value)
 
 
+# what the last build_capi / build_torch_binding call did with each artefact: "compiled" or "reused" (the stamp next to
+# the binary equals the digest of its sources, headers and flags, i.e. it was built from exactly these sources)
+ACTIONS = {}
+
+
 def _run(cmd, verbose):
     if verbose:
         print("+", " ".join(map(str, cmd)), flush=True)
@@ -83,11 +91,14 @@ def build_capi(force: bool = False, verbose: bool = False) -> Path:
     out = capi_path()
     srcs = [CSRC / s for s in CAPI_SOURCES]
     deps = srcs + [CSRC / d for d in CAPI_DEPS] + [INCLUDE / "msda_b200.h"]
-    stamp = _digest(deps, ARCH_FLAGS + NVCC_FLAGS)
+    stamp = _digest(deps, ARCH_FLAGS + NVCC_FLAGS + LINK_FLAGS)
     if force or _stale(out, stamp):
-        cmd = [_nvcc(), *ARCH_FLAGS, *NVCC_FLAGS, "-shared", "-Xcompiler", "-fPIC", "-o", out, *srcs]
+        cmd = [_nvcc(), *ARCH_FLAGS, *NVCC_FLAGS, *LINK_FLAGS, "-shared", "-Xcompiler", "-fPIC", "-o", out, *srcs]
         _run(cmd, verbose)
         _write_stamp(out, stamp)
+        ACTIONS[out.name] = "compiled" + (" (forced)" if force else "")
+    else:
+        ACTIONS[out.name] = f"reused: stamp {stamp[:12]} matches the digest of the sources, headers and flags"
     return out
 
 
@@ -115,6 +126,9 @@ def build_torch_binding(force: bool = False, verbose: bool = False) -> Path:
                "-lmsda_b200", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{torch_lib}", f"-Wl,-rpath,{cuda_home / 'lib64'}"]
         _run(cmd, verbose)
         _write_stamp(out, stamp)
+        ACTIONS[out.name] = "compiled" + (" (forced)" if force else "")
+    else:
+        ACTIONS[out.name] = f"reused: stamp {stamp[:12]} matches the digest of the sources, headers and flags"
     return out
 
 
@@ -126,7 +140,7 @@ def build_variant(name: str, defines, verbose: bool = False) -> Path:
     vdir.mkdir(parents=True, exist_ok=True)
     out = vdir / "libmsda_b200.so"
     srcs = [CSRC / s for s in CAPI_SOURCES]
-    cmd = [_nvcc(), *ARCH_FLAGS, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-Xcompiler", "-fPIC",
+    cmd = [_nvcc(), *ARCH_FLAGS, *NVCC_FLAGS, *LINK_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-Xcompiler", "-fPIC",
            "-o", out, *srcs]
     _run(cmd, verbose)
     shutil.copy2(module_path(), vdir / module_path().name)

@@ -35,9 +35,6 @@ PROTOTYPES = {
     "msda_topk_samples": (C.c_int, [C.POINTER(msda_shape), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "msda_forward": (C.c_int, [_SH, _P, _I64P, _I64P, _P, _P, _P, _P]),
-    "msda_forward_workspace_bytes": (C.c_size_t, [_SH]),
-    "msda_forward_ws": (C.c_int, [_SH, _P, _I64P, _I64P, _P, _P, _P, _P, C.c_size_t, _P]),
-    "msda_tile_mode": (C.c_int, [C.c_int]),
     "msda_backward_workspace_bytes": (C.c_size_t, [_SH]),
     "msda_backward": (C.c_int, [_SH, _P, _I64P, _I64P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "msda_forward_3d": (C.c_int, [_SH, C.c_int64, _P, _I64P, _I64P, _P, _P, _P, _P]),
@@ -123,8 +120,8 @@ def _stream_ptr(t):
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out=None, use_workspace=True):
-    """msda_forward_ws on CUDA torch tensors through the C ABI (no torch binding involved)."""
+def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, out=None):
+    """msda_forward on CUDA torch tensors through the C ABI (no torch binding involved)."""
     import torch
     lib = load()
     if not value.is_cuda:
@@ -133,13 +130,10 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
     if out is None:
         out = torch.empty(value.shape[0], sampling_loc.shape[1], value.shape[2] * value.shape[3],
                           dtype=value.dtype, device=value.device)
-    ws_bytes = lib.msda_forward_workspace_bytes(C.byref(sh)) if use_workspace else 0
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
     with torch.cuda.device(value.device):
-        check(lib.msda_forward_ws(C.byref(sh), value.data_ptr(), spatial_shapes.data_ptr(),
-                                  level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
-                                  out.data_ptr(), ws.data_ptr() if ws is not None else None, ws_bytes,
-                                  _stream_ptr(value)), "msda_forward")
+        check(lib.msda_forward(C.byref(sh), value.data_ptr(), spatial_shapes.data_ptr(),
+                               level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                               out.data_ptr(), _stream_ptr(value)), "msda_forward")
     return out
 
 
@@ -154,7 +148,7 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     gl = torch.empty_like(sampling_loc)
     ga = torch.empty_like(attn_weight)
     ws_bytes = lib.msda_backward_workspace_bytes(C.byref(sh)) if use_workspace else 0
-    ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
     with torch.cuda.device(value.device):
         check(lib.msda_backward(C.byref(sh), value.data_ptr(), spatial_shapes.data_ptr(),
                                 level_start_index.data_ptr(), sampling_loc.data_ptr(), attn_weight.data_ptr(),

@@ -4,7 +4,6 @@
 
 #include "../../include/msda_b200.h"
 #include "msda_kernels.cuh"
-#include "msda_tile_kernels.cuh"
 
 #include <atomic>
 #include <algorithm>
@@ -103,124 +102,6 @@ unsigned generic_grid(int64_t warps, int threads)
     const int sms = sm_count_aux();
     const int64_t need = (warps + threads / 32 - 1) / (threads / 32);
     return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(need, int64_t(sms) * 32)));
-}
-
-
-// ---- persistent tile kernels (msda_tile_kernels.cuh) ------------------------------------------
-
-// MSDA_TILE=0 keeps every call on the one-shot kernels, MSDA_TILE=1 forces the persistent kernels
-// wherever they are applicable (tests use it to cover them at small sizes); default: by size.
-std::atomic<int> g_tile_mode{-2};
-int tile_mode()
-{
-    int mode = g_tile_mode.load();
-    if (mode == -2) {
-        const char *e = std::getenv("MSDA_TILE");
-        mode = e ? std::atoi(e) : -1;
-        g_tile_mode.store(mode);
-    }
-    return mode;
-}
-int tile_batch()
-{
-    static int b = 0;
-    if (!b) {
-        const char *e = std::getenv("MSDA_TILE_BATCH");
-        b = e ? std::max(1, std::atoi(e)) : 4;
-    }
-    return b;
-}
-
-struct TilePlan {
-    bool ok = false;
-    int grid = 0, n_units = 0, segs_per_unit = 0, n_segs = 0;
-    size_t ctr_bytes = 0;
-};
-
-// TCE geometry only: 8 heads x 32 channels, 4 levels x 4 points; fp32 locations.
-TilePlan tile_plan(const Dims &d, bool backward)
-{
-    TilePlan t;
-    if (tile_mode() == 0) return t;
-    if (!(d.M == 8 && d.D == 32 && d.L == 4 && d.P == 4 && d.ldt == MSDA_F32)) return t;
-    if (backward ? !(d.vdt == MSDA_F32 || d.vdt == MSDA_BF16) : d.vdt != MSDA_F32) return t;
-    if (d.S * 8 * 32 * 4 >= (int64_t(1) << 31) || d.Lq >= (int64_t(1) << 30) || d.N >= (int64_t(1) << 22)) return t;
-    if (d.N * d.Lq == 0) return t;
-    const int sms = sm_count_aux();
-    // worth it only when every SM gets a few hundred queries (the flush / staging of a unit is a fixed cost)
-    if (tile_mode() != 1 && (d.N * d.Lq * 2 < int64_t(sms) * 256 || d.Lq < 256)) return t;
-    t.n_units = static_cast<int>(d.N * 2);
-    t.segs_per_unit = t.n_units >= sms ? 1 : std::max(1, sms / t.n_units);
-    t.segs_per_unit = static_cast<int>(std::min<int64_t>(t.segs_per_unit, std::max<int64_t>(1, d.Lq)));
-    t.n_segs = t.n_units * t.segs_per_unit;
-    t.grid = std::min(sms, t.n_segs);
-    t.ctr_bytes = (static_cast<size_t>(t.n_segs) * 2 * sizeof(int) + 255) & ~size_t(255);
-    t.ok = true;
-    return t;
-}
-
-int tile_smem_optin()
-{
-    static int v = 0;
-    if (!v) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        if (v <= 0) v = 48 * 1024;
-    }
-    return v;
-}
-
-msda::TileParams tile_params(const Dims &d, const TilePlan &t, int nwarps, void *ctr, size_t &smem)
-{
-    msda::TileParams tp;
-    tp.Lq = d.Lq; tp.S = d.S;
-    tp.n_units = t.n_units; tp.segs_per_unit = t.segs_per_unit; tp.n_segs = t.n_segs;
-    tp.batch = tile_batch();
-    const int table = nwarps * 1024;
-    const int budget = tile_smem_optin() - 1024 - table - msda::kTileRowBytes; // 1 KB static control block, one scratch row
-    tp.cap_rows = static_cast<int>(std::min<int64_t>(std::max(0, budget / msda::kTileRowBytes), d.S));
-    if (const char *e = std::getenv("MSDA_TILE_CAP")) tp.cap_rows = std::min(tp.cap_rows, std::max(0, std::atoi(e)));   // tuning aid
-    tp.ctr = static_cast<int *>(ctr);
-    smem = static_cast<size_t>(tp.cap_rows + 1) * msda::kTileRowBytes + table;
-    return tp;
-}
-
-template <typename VT>
-int launch_bwd_tile(const Dims &d, const TilePlan &t, const void *value, const int64_t *shapes, const int64_t *lsi,
-                    const void *loc, const void *aw, const void *go, float *gv, void *gl, void *ga, void *ctr,
-                    cudaStream_t st)
-{
-    constexpr int NW = MSDA_TILE_BWD_WARPS;
-    auto kern = msda::bwd_tile_kernel<VT, float, NW>;
-    size_t smem = 0;
-    const msda::TileParams tp = tile_params(d, t, NW, ctr, smem);
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (ce != cudaSuccess) return static_cast<int>(ce);
-    ce = cudaMemsetAsync(ctr, 0, t.ctr_bytes, st);
-    if (ce != cudaSuccess) return static_cast<int>(ce);
-    kern<<<t.grid, NW * 32, smem, st>>>(static_cast<const VT *>(value), shapes, lsi, static_cast<const float *>(loc),
-                                        static_cast<const float *>(aw), static_cast<const VT *>(go), gv,
-                                        static_cast<float *>(gl), static_cast<float *>(ga), tp);
-    ++g_launches;
-    return launch_status();
-}
-
-int launch_fwd_tile(const Dims &d, const TilePlan &t, const void *value, const int64_t *shapes, const int64_t *lsi,
-                    const void *loc, const void *aw, void *out, void *ctr, cudaStream_t st)
-{
-    constexpr int NW = MSDA_TILE_FWD_WARPS;
-    auto kern = msda::fwd_tile_kernel<float, NW>;
-    size_t smem = 0;
-    const msda::TileParams tp = tile_params(d, t, NW, ctr, smem);
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (ce != cudaSuccess) return static_cast<int>(ce);
-    ce = cudaMemsetAsync(ctr, 0, t.ctr_bytes, st);
-    if (ce != cudaSuccess) return static_cast<int>(ce);
-    kern<<<t.grid, NW * 32, smem, st>>>(static_cast<const float *>(value), shapes, lsi, static_cast<const float *>(loc),
-                                        static_cast<const float *>(aw), static_cast<float *>(out), tp);
-    ++g_launches;
-    return launch_status();
 }
 
 // ---- forward ------------------------------------------------------------------------------
@@ -375,7 +256,6 @@ int backward_impl(const msda_shape *shape, int64_t group, const void *value, con
     const int64_t nval = d.N * d.S * d.M * d.D;
     const bool sixteen = (d.vdt == MSDA_BF16 || d.vdt == MSDA_F16);
     const bool use_ws = sixteen && ws != nullptr;
-    const size_t scratch_bytes = sixteen ? ((static_cast<size_t>(nval) * sizeof(float) + 255) & ~size_t(255)) : 0;
     if (use_ws && ws_bytes < static_cast<size_t>(nval) * sizeof(float)) return MSDA_E_WORKSPACE;
 
     // the only zero-fill pass: grad_value (or its fp32 scratch).  grad_loc / grad_aw are
@@ -389,16 +269,6 @@ int backward_impl(const msda_shape *shape, int64_t group, const void *value, con
     const bool fast = !THREE_D && fast_eligible(d) && aligned16(value) && aligned16(loc) && aligned16(aw) &&
                       aligned16(go) && aligned16(gv) && aligned16(gl) && aligned16(ga) && (!use_ws || aligned16(ws));
     if (fast) {
-        // persistent kernels for the encoder-sized calls: need the grab counters behind the scratch
-        const TilePlan plan = THREE_D ? TilePlan{} : tile_plan(d, true);
-        if (plan.ok && ws != nullptr && ws_bytes >= scratch_bytes + plan.ctr_bytes && (!sixteen || use_ws)) {
-            void *ctr = static_cast<char *>(ws) + scratch_bytes;
-            if (d.vdt == MSDA_F32)
-                return launch_bwd_tile<float>(d, plan, value, shapes, lsi, loc, aw, go, static_cast<float *>(gv), gl, ga, ctr, st);
-            e = launch_bwd_tile<__nv_bfloat16>(d, plan, value, shapes, lsi, loc, aw, go, static_cast<float *>(ws), gl, ga, ctr, st);
-            if (e) return e;
-            return launch_cast<__nv_bfloat16>(static_cast<const float *>(ws), gv, nval, st);
-        }
         if (d.vdt == MSDA_F32)
             return launch_bwd_fast<float, float, float>(d, value, shapes, lsi, loc, aw, go, static_cast<float *>(gv), gl, ga, st);
         if (d.vdt == MSDA_BF16) {
@@ -469,10 +339,6 @@ const char *msda_kernel_name(const msda_shape *shape, int backward)
     Dims d;
     if (check_shape(shape, d)) return "invalid";
     if (fast_eligible(d)) {
-        if (tile_plan(d, backward != 0).ok) {      // what a call WITH a workspace runs
-            if (d.vdt == MSDA_F32) return backward ? "bwd_tile_d32_f32" : "fwd_tile_d32_f32";
-            return "bwd_tile_d32_bf16";
-        }
         if (d.vdt == MSDA_F32) return backward ? "bwd_fast_d32_f32" : "fwd_fast_d32_f32";
         return backward ? "bwd_fast_d32_bf16" : "fwd_fast_d32_bf16";
     }
@@ -505,28 +371,8 @@ int msda_check_im2col_step(int64_t n_frames, int im2col_step)
 
 int64_t msda_launch_count(void) { return g_launches.load(); }
 
-int msda_tile_mode(int mode)
-{
-    const int prev = tile_mode();
-    if (mode >= -1 && mode <= 1) g_tile_mode.store(mode);
-    return prev;
-}
-
-size_t msda_forward_workspace_bytes(const msda_shape *shape)
-{
-    Dims d;
-    if (check_shape(shape, d) || !fast_eligible(d)) return 0;
-    return tile_plan(d, false).ctr_bytes;
-}
-
 int msda_forward(const msda_shape *shape, const void *value, const int64_t *shapes, const int64_t *lsi,
                  const void *loc, const void *aw, void *out, void *stream)
-{
-    return msda_forward_ws(shape, value, shapes, lsi, loc, aw, out, nullptr, 0, stream);
-}
-
-int msda_forward_ws(const msda_shape *shape, const void *value, const int64_t *shapes, const int64_t *lsi,
-                    const void *loc, const void *aw, void *out, void *ws, size_t ws_bytes, void *stream)
 {
     Dims d;
     const int e = check_shape(shape, d);
@@ -535,9 +381,6 @@ int msda_forward_ws(const msda_shape *shape, const void *value, const int64_t *s
     if (!value || !shapes || !lsi || !loc || !aw || !out) return MSDA_E_NULL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (fast_eligible(d) && aligned16(value) && aligned16(loc) && aligned16(aw) && aligned16(out)) {
-        const TilePlan plan = tile_plan(d, false);
-        if (plan.ok && ws != nullptr && ws_bytes >= plan.ctr_bytes)
-            return launch_fwd_tile(d, plan, value, shapes, lsi, loc, aw, out, ws, st);
         if (d.vdt == MSDA_F32) return launch_fwd_fast<float, float>(d, value, shapes, lsi, loc, aw, out, st);
         if (d.ldt == MSDA_F32) return launch_fwd_fast<__nv_bfloat16, float>(d, value, shapes, lsi, loc, aw, out, st);
         return launch_fwd_fast<__nv_bfloat16, __nv_bfloat16>(d, value, shapes, lsi, loc, aw, out, st);
@@ -549,10 +392,8 @@ size_t msda_backward_workspace_bytes(const msda_shape *shape)
 {
     Dims d;
     if (check_shape(shape, d)) return 0;
-    size_t bytes = 0;
-    if (d.vdt == MSDA_BF16 || d.vdt == MSDA_F16) bytes = (static_cast<size_t>(d.N * d.S * d.M * d.D) * sizeof(float) + 255) & ~size_t(255);
-    if (fast_eligible(d)) bytes += tile_plan(d, true).ctr_bytes;      // grab counters of the persistent kernel
-    return bytes;
+    if (d.vdt == MSDA_BF16 || d.vdt == MSDA_F16) return static_cast<size_t>(d.N * d.S * d.M * d.D) * sizeof(float);
+    return 0;
 }
 
 int msda_backward(const msda_shape *shape, const void *value, const int64_t *shapes, const int64_t *lsi,

@@ -65,6 +65,16 @@ int host_pipeline(msda_host_ctx *c, const msda_shape *shape, const void *value, 
     int prev = 0;
     MSDA_CU(cudaGetDevice(&prev));
     MSDA_CU(cudaSetDevice(c->device));
+    // Every exit below restores the caller's device; an exit on an error first drains the three streams, because
+    // copies and kernels of earlier chunks may still be using the caller's host buffers and the staging.
+    struct Guard {
+        msda_host_ctx *c; int prev; bool done = false;
+        ~Guard()
+        {
+            if (!done) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->s_run); cudaStreamSynchronize(c->s_out); }
+            cudaSetDevice(prev);
+        }
+    } guard{c, prev};
 
     const size_t ev = dtype_size(d.vdt), el = dtype_size(d.ldt);
     const size_t f_val = static_cast<size_t>(d.S) * d.M * d.D * ev;            // bytes per frame
@@ -78,12 +88,12 @@ int host_pipeline(msda_host_ctx *c, const msda_shape *shape, const void *value, 
     if ((rc = ctx_reserve(c, B_VALUE, N * f_val)) || (rc = ctx_reserve(c, B_LOC, N * f_loc)) ||
         (rc = ctx_reserve(c, B_AW, N * f_aw)) || (rc = ctx_reserve(c, B_OUT, N * f_out)) ||
         (rc = ctx_reserve(c, B_SHAPES, sizeof(int64_t) * 2 * d.L)) || (rc = ctx_reserve(c, B_LSI, sizeof(int64_t) * d.L)))
-        { cudaSetDevice(prev); return rc; }
+        return rc;
     if (with_backward) {
         if ((rc = ctx_reserve(c, B_GO, N * f_out)) || (rc = ctx_reserve(c, B_GV, N * f_val)) ||
             (rc = ctx_reserve(c, B_GL, N * f_loc)) || (rc = ctx_reserve(c, B_GA, N * f_aw)) ||
             (need_ws && (rc = ctx_reserve(c, B_WS, static_cast<size_t>(d.S) * d.M * d.D * sizeof(float) * N))))
-            { cudaSetDevice(prev); return rc; }
+            return rc;
     }
 
     // chunking: up to 16 chunks (MSDA_HOST_CHUNKS overrides, for tuning), at least one frame each
@@ -94,7 +104,7 @@ int host_pipeline(msda_host_ctx *c, const msda_shape *shape, const void *value, 
     }();
     const int64_t n_chunks = std::max<int64_t>(1, std::min<int64_t>(d.N, max_chunks));
     const int64_t per = (d.N + n_chunks - 1) / n_chunks;
-    if ((rc = ctx_events(c, static_cast<size_t>(n_chunks)))) { cudaSetDevice(prev); return rc; }
+    if ((rc = ctx_events(c, static_cast<size_t>(n_chunks)))) return rc;
 
     MSDA_CU(cudaMemcpyAsync(c->buf[B_SHAPES], shapes_h, sizeof(int64_t) * 2 * d.L, cudaMemcpyHostToDevice, c->s_in));
     MSDA_CU(cudaMemcpyAsync(c->buf[B_LSI], lsi_h, sizeof(int64_t) * d.L, cudaMemcpyHostToDevice, c->s_in));
@@ -119,7 +129,7 @@ int host_pipeline(msda_host_ctx *c, const msda_shape *shape, const void *value, 
         e = msda_forward(&sub, at(c->buf[B_VALUE], o * f_val), static_cast<const int64_t *>(c->buf[B_SHAPES]),
                          static_cast<const int64_t *>(c->buf[B_LSI]), at(c->buf[B_LOC], o * f_loc),
                          at(c->buf[B_AW], o * f_aw), at(c->buf[B_OUT], o * f_out), c->s_run);
-        if (e) { cudaSetDevice(prev); return e; }
+        if (e) return e;
         if (with_backward) {
             const size_t f_ws = static_cast<size_t>(d.S) * d.M * d.D * sizeof(float);
             e = msda_backward(&sub, at(c->buf[B_VALUE], o * f_val), static_cast<const int64_t *>(c->buf[B_SHAPES]),
@@ -127,7 +137,7 @@ int host_pipeline(msda_host_ctx *c, const msda_shape *shape, const void *value, 
                               at(c->buf[B_AW], o * f_aw), at(c->buf[B_GO], o * f_out), at(c->buf[B_GV], o * f_val),
                               at(c->buf[B_GL], o * f_loc), at(c->buf[B_GA], o * f_aw),
                               need_ws ? at(c->buf[B_WS], o * f_ws) : nullptr, need_ws ? nf * f_ws : 0, c->s_run);
-            if (e) { cudaSetDevice(prev); return e; }
+            if (e) return e;
         }
         MSDA_CU(cudaEventRecord(c->ev_run[ci], c->s_run));
 
@@ -142,7 +152,7 @@ int host_pipeline(msda_host_ctx *c, const msda_shape *shape, const void *value, 
     MSDA_CU(cudaStreamSynchronize(c->s_out));
     MSDA_CU(cudaStreamSynchronize(c->s_run));
     MSDA_CU(cudaStreamSynchronize(c->s_in));
-    cudaSetDevice(prev);
+    guard.done = true;
     return MSDA_OK;
 }
 

@@ -148,6 +148,10 @@ template <> struct FastCfg<__nv_bfloat16> {
 #ifndef MSDA_FWD_BATCH
 #define MSDA_FWD_BATCH 2
 #endif
+#ifndef MSDA_TABLE
+#define MSDA_TABLE 0   // 1: a point's weights reach the other lanes of its head through a per-warp table in
+                       // shared memory (one broadcast LDS.128 per point); 0: four shuffles per point
+#endif
 #ifndef MSDA_EXP
 #define MSDA_EXP 0     // timing experiments only (tools/variants.py); 0 = product
 #endif
@@ -377,6 +381,26 @@ __device__ __forceinline__ PointView view_point(const OwnedPoint &o, int src)
     return v;
 }
 
+// The same hand-over through shared memory: the owner lane stores (ta, tb, lw, packed) of its points once
+// (16 bytes each), every lane of the head reads a point back with ONE broadcast LDS.128 — 4 different
+// addresses per warp = one wavefront of the L1TEX data pipe instead of four SHFL passes (the pipe is what
+// bounds both fast kernels).  Table layout: [point][head of the warp].
+__device__ __forceinline__ void table_put(float4 *table, int slot, const OwnedPoint &o)
+{
+    table[slot] = make_float4(o.ta, o.tb, o.lw, __int_as_float(o.packed));
+}
+__device__ __forceinline__ PointView table_view(const float4 *table, int slot)
+{
+    const float4 d = table[slot];
+    const float hw = 1.f - d.z;
+    PointView v;
+    v.w0 = d.x * hw; v.w1 = d.x * d.z; v.w2 = d.y * hw; v.w3 = d.y * d.z;
+    const int packed = __float_as_int(d.w);
+    v.base = packed >> 4;
+    v.mask = packed & 15;
+    return v;
+}
+
 // --------------------------------------------------------------------------------------------
 // Fused module prologue (models/ops/modules/ms_deform_attn.py:99-109).  In PROLOGUE mode the
 // `loc` / `aw` kernel arguments are the RAW outputs of the two Linear layers (sampling offsets
@@ -507,6 +531,13 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 #pragma unroll
     for (int pp = 0; pp < PPL; ++pp)
         own[pp] = own_point(xy[2 * pp], xy[2 * pp + 1], a[pp], Hs[pp], Ws[pp], starts[pp]);
+#if MSDA_TABLE
+    __shared__ float4 point_table[8][kFastLP * HPW];
+    float4 *table = point_table[threadIdx.x >> 5];
+#pragma unroll
+    for (int pp = 0; pp < PPL; ++pp) table_put(table, (j * PPL + pp) * HPW + g, own[pp]);
+    __syncwarp();
+#endif
 
     // All offsets inside a frame are 32-bit byte offsets.
     const int pix = M * kFastD;                            // elements between neighbouring pixels
@@ -535,6 +566,8 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 #if MSDA_EXP == 4
             pv[b].w0 = own[pp].ta; pv[b].w1 = own[pp].tb; pv[b].w2 = own[pp].lw; pv[b].w3 = own[pp].lw;
             pv[b].base = own[pp].packed >> 4; pv[b].mask = own[pp].packed & 15;
+#elif MSDA_TABLE
+            pv[b] = table_view(table, p * HPW + g);
 #else
             pv[b] = view_point<LPH>(own[pp], src);
 #endif
@@ -696,6 +729,13 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 #pragma unroll
     for (int pp = 0; pp < PPL; ++pp)
         own[pp] = own_point(xy[2 * pp], xy[2 * pp + 1], a[pp], Hs[pp], Ws[pp], starts[pp]);
+#if MSDA_TABLE
+    __shared__ float4 point_table[8][kFastLP * HPW];
+    float4 *table = point_table[threadIdx.x >> 5];
+#pragma unroll
+    for (int pp = 0; pp < PPL; ++pp) table_put(table, (j * PPL + pp) * HPW + g, own[pp]);
+    __syncwarp();
+#endif
 
     const int pix = M * kFastD;
     const int pixb = pix * static_cast<int>(sizeof(VT));
@@ -713,7 +753,11 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     auto leaf = [&](auto pc, float (&d)[4]) {
         constexpr int p = decltype(pc)::value;
         constexpr int src = p / PPL, pp = p % PPL;
+#if MSDA_TABLE
+        const PointView pv = table_view(table, p * HPW + g);
+#else
         const PointView pv = view_point<LPH>(own[pp], src);
+#endif
         const int W = TCE ? rowW[p >> 2] : __shfl_sync(kFull, own[pp].W, src, LPH);
         const char *r0 = vlane + static_cast<int64_t>(pv.base) * pixb;
         const char *r1 = r0 + static_cast<int64_t>(W) * pixb;

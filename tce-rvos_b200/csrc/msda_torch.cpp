@@ -125,15 +125,10 @@ at::Tensor ms_deform_attn_forward(const at::Tensor &value, const at::Tensor &spa
         rc = msda_forward_3d(&p.shape, p.step, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
                              level_start_index.data_ptr<int64_t>(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
                              out.data_ptr(), stream_of(value));
-    else {
-        // grab counters of the persistent kernel (a few hundred bytes from the caching allocator; 0 for small calls)
-        at::Tensor ws;
-        const size_t ws_bytes = msda_forward_workspace_bytes(&p.shape);
-        if (ws_bytes) ws = at::empty({static_cast<int64_t>(ws_bytes)}, value.options().dtype(at::kByte));
-        rc = msda_forward_ws(&p.shape, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
-                             level_start_index.data_ptr<int64_t>(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
-                             out.data_ptr(), ws_bytes ? ws.data_ptr() : nullptr, ws_bytes, stream_of(value));
-    }
+    else
+        rc = msda_forward(&p.shape, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
+                          level_start_index.data_ptr<int64_t>(), sampling_loc.data_ptr(), attn_weight.data_ptr(),
+                          out.data_ptr(), stream_of(value));
     check_rc(rc, "ms_deform_attn_forward");
     return out;
 }
@@ -157,7 +152,7 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor &value, const a
     at::Tensor grad_aw = at::empty_like(attn_weight);
     at::Tensor ws;
     const size_t ws_bytes = msda_backward_workspace_bytes(&p.shape);
-    if (ws_bytes) ws = at::empty({static_cast<int64_t>((ws_bytes + 3) / sizeof(float))}, value.options().dtype(at::kFloat));
+    if (ws_bytes) ws = at::empty({static_cast<int64_t>(ws_bytes / sizeof(float))}, value.options().dtype(at::kFloat));
     int rc;
     if (is_3d)
         rc = msda_backward_3d(&p.shape, p.step, value.data_ptr(), spatial_shapes.data_ptr<int64_t>(),
@@ -226,6 +221,13 @@ bool ms_deform_attn_prologue_supported(const at::Tensor &value, const at::Tensor
     };
     s.value_dtype = code(value.scalar_type());
     s.loc_dtype = code(offsets.scalar_type());
+    // The fused kernels take 16-byte vectors and msda_prologue_* reject misaligned pointers (MSDA_E_ALIGN) instead of
+    // falling back.  A contiguous view with a storage offset keeps its address through .contiguous(), so answer "no"
+    // here and let the caller compose the prologue itself (msda_forward / msda_backward handle any alignment).
+    auto misaligned = [](const at::Tensor &t) {
+        return t.is_contiguous() && (reinterpret_cast<uintptr_t>(t.data_ptr()) & 15u) != 0;
+    };
+    if (misaligned(value) || misaligned(offsets) || misaligned(ref_points)) return false;
     return msda_prologue_supported(&s, static_cast<int>(ref_points.size(3))) != 0;
 }
 

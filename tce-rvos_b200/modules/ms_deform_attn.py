@@ -23,6 +23,7 @@ What differs:
 from __future__ import annotations
 
 import math
+import weakref
 import warnings
 
 import torch
@@ -32,6 +33,8 @@ from torch.nn.init import constant_, xavier_uniform_
 
 from ..functions import MSDeformAttnFunction, MSDeformAttnPrologueFunction, MSDeformAttnValueEpilogue
 from .._ext import load as _load_ext
+
+_CHECKED_SHAPES = {}      # (id, version, Len_in) -> weakref of a validated spatial_shapes tensor (check_shapes='once')
 
 
 def _is_power_of_2(n):
@@ -68,7 +71,6 @@ class MSDeformAttn(nn.Module):
         self.fused_value_epilogue = False
         self.value_dtype = None             # None = keep value_proj's dtype | torch.bfloat16
         self.check_shapes = "once"          # True | False | "once"
-        self._checked = set()
 
         self._reset_parameters()
 
@@ -93,12 +95,18 @@ class MSDeformAttn(nn.Module):
         if self.check_shapes is False:
             return
         if self.check_shapes == "once":
-            key = (input_spatial_shapes.data_ptr(), int(Len_in), input_spatial_shapes.device)
-            if key in self._checked:
+            # keyed on the tensor OBJECT and its version counter, not on its address: the caching allocator hands
+            # the same pointer to a later, different shape table, which must be checked again (the kernels trust
+            # H*W and level_start_index).  The model builds the table once per forward and passes the same tensor
+            # to every layer (tce_deformable_transformer.py:173-181); the cache is shared by all MSDeformAttn
+            # instances, so one sync per forward remains.
+            key = (id(input_spatial_shapes), input_spatial_shapes._version, int(Len_in))
+            hit = _CHECKED_SHAPES.get(key)
+            if hit is not None and hit() is input_spatial_shapes:
                 return
-            if len(self._checked) > 64:
-                self._checked.clear()
-            self._checked.add(key)
+            if len(_CHECKED_SHAPES) > 64:
+                _CHECKED_SHAPES.clear()
+            _CHECKED_SHAPES[key] = weakref.ref(input_spatial_shapes)
         assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,

@@ -37,30 +37,18 @@ def test_library_exports_every_declared_symbol(capi):
 
 def test_introspection(capi):
     lib = capi.load()
-    assert lib.msda_abi_version() == 2
+    assert lib.msda_abi_version() == 1
     assert b"im2col_step" in lib.msda_error_string(capi.MSDA_E_IM2COL_STEP)
     sh = capi.make_shape(10, 4820, 4820, 8, 32, 4, 4, capi.MSDA_F32, capi.MSDA_F32)
     # SURVEY.md 8d worked example: fwd 172.7 MB, fwd+bwd 468.9 MB at config 2
     assert lib.msda_algorithmic_bytes(sh, 0) == 4 * 10 * (256 * 4820 + 640 * 4820)
     assert lib.msda_algorithmic_bytes(sh, 2) == 4 * 10 * (768 * 4820 + 1664 * 4820)
-    # encoder-sized calls at the TCE geometry run on the persistent kernels (given a workspace) ...
-    assert lib.msda_kernel_name(sh, 0) == b"fwd_tile_d32_f32"
-    assert lib.msda_kernel_name(sh, 1) == b"bwd_tile_d32_f32"
+    assert lib.msda_kernel_name(sh, 0) == b"fwd_fast_d32_f32"
+    assert lib.msda_kernel_name(sh, 1) == b"bwd_fast_d32_f32"
     sh16 = capi.make_shape(10, 4820, 4820, 8, 32, 4, 4, capi.MSDA_BF16, capi.MSDA_F32)
     assert lib.msda_kernel_name(sh16, 0) == b"fwd_fast_d32_bf16"
-    assert lib.msda_kernel_name(sh16, 1) == b"bwd_tile_d32_bf16"
-    # ... whose workspace is the grab counters (2 ints per segment, 256-byte granules) behind the fp32 scratch
-    ctr = lib.msda_forward_workspace_bytes(sh)
-    assert 0 < ctr <= 4096 and ctr % 256 == 0
-    assert lib.msda_backward_workspace_bytes(sh) == ctr
-    assert lib.msda_backward_workspace_bytes(sh16) == 10 * 4820 * 256 * 4 + ctr
-    # ... while decoder-sized calls stay on the one-shot kernels and need no counters
-    small = capi.make_shape(36, 4820, 5, 8, 32, 4, 4, capi.MSDA_F32, capi.MSDA_F32)
-    assert lib.msda_kernel_name(small, 1) == b"bwd_fast_d32_f32"
-    assert lib.msda_forward_workspace_bytes(small) == 0 and lib.msda_backward_workspace_bytes(small) == 0
-    prev = lib.msda_tile_mode(0)
-    assert lib.msda_kernel_name(sh, 1) == b"bwd_fast_d32_f32" and lib.msda_backward_workspace_bytes(sh) == 0
-    assert lib.msda_tile_mode(prev) == 0
+    assert lib.msda_backward_workspace_bytes(sh16) == 10 * 4820 * 256 * 4
+    assert lib.msda_backward_workspace_bytes(sh) == 0
     odd = capi.make_shape(1, 30, 2, 2, 71, 2, 2, capi.MSDA_F64, capi.MSDA_F64)
     assert lib.msda_kernel_name(odd, 1) == b"bwd_generic"
     assert lib.msda_prologue_supported(sh, 2) == 1 and lib.msda_prologue_supported(sh, 3) == 0
@@ -211,7 +199,7 @@ def test_header_is_plain_c_and_links(tmp_path, capi):
                     f"-L{lib.parent}", "-lmsda_b200", f"-Wl,-rpath,{lib.parent}", "-Wl,-rpath,/usr/local/cuda/lib64"],
                    check=True, capture_output=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out == ["2", "bwd_tile_d32_f32", str(4 * 10 * (768 * 4820 + 1664 * 4820)), str(capi.MSDA_E_NULL)]
+    assert out == ["1", "bwd_fast_d32_f32", str(4 * 10 * (768 * 4820 + 1664 * 4820)), str(capi.MSDA_E_NULL)]
 
 
 @pytest.mark.skipif(not REF.exists(), reason="reference tree not present on this machine")

@@ -475,6 +475,34 @@ def test_against_reference_cuda_extension(pkg, oracle, kind):
     assert oracle.max_rel(go[1].cpu(), gr[1].cpu()) < 2e-5       # grad_sampling_loc
 
 
+@pytest.mark.parametrize("kind,frames,step", [("model", 4, 2), ("testpy", 6, 3), ("testpy", 5, 64)])
+def test_3d_variant_against_reference_cuda_extension(pkg, oracle, kind, frames, step):
+    """Pins the fork's cross-frame variant (MSDeformAttnFunction3D, is_3d=True) to the reference itself: the
+    reference has this path only as CUDA (ms_deform_im2col_cuda.cuh:366-420 forward, :565-712 backward), so its
+    own kernels, compiled for sm_100 under baseline/_ref, are the ground truth here — forward and all three
+    gradients, including the chunk-relative frame blend of the im2col_step loop (ms_deform_attn_cuda.cu:54,77)
+    and a chunk of ONE group when step >= N."""
+    ref = _reference_cuda()
+    if ref is None:
+        pytest.skip("baseline/_ref/MSDA_reference_cuda.so not built")
+    levels = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    inp = oracle.make_inputs(kind, frames, levels, Lq=301, M=8, D=32, P=4, seed=21, three_d=True)
+    t = dev_inputs(inp, torch.float32)
+    ext = pkg.load_extension()
+    args = (t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    out_r = ref.ms_deform_attn_forward(*args, step, True)
+    out_o = ext.ms_deform_attn_forward(*args, step, True)
+    gr = ref.ms_deform_attn_backward(*args, t["grad_out"], step, True)
+    go = ext.ms_deform_attn_backward(*args, t["grad_out"], step, True)
+    torch.cuda.synchronize()
+    assert float(out_r.abs().max()) > 0
+    assert oracle.max_rel(out_o.cpu(), out_r.cpu()) < 2e-6
+    assert oracle.max_rel(go[0].cpu(), gr[0].cpu()) < 5e-6       # grad_value (atomic order differs)
+    assert oracle.max_rel(go[2].cpu(), gr[2].cpu()) < 5e-6       # grad_attn_weight
+    assert go[1].shape == gr[1].shape and go[1].shape[-1] == 3
+    assert oracle.max_rel(go[1].cpu(), gr[1].cpu()) < 2e-5       # grad_sampling_loc incl. the frame coordinate
+
+
 # ------------------------------------------------------------------------------------------------
 # 64-bit addressing at the top of the scaling sweep (BASELINE.json config 5: N = 1024 at 512x896)
 # ------------------------------------------------------------------------------------------------
@@ -689,3 +717,44 @@ def test_sixteen_bit_generic_kernels(capi, oracle, vdt, ldt):
     eps = 1e-4 if ldt == torch.float32 else 5e-3
     check_grads(oracle, (gv.float(), gl.float(), ga.float()), (rv, rl, ra), t["loc"].float().cpu(), levels, tol if ldt == torch.float32 else 1e-2,
                 eps_px=eps, stress=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# non-finite / overflowing sampling locations
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["fast", "generic"])
+def test_non_finite_and_overflowing_locations_contribute_nothing(capi, oracle, path):
+    """A sampling point whose location is inf / NaN / overflows when scaled is gated off by the reference
+    (ms_deform_im2col_cuda.cuh:441: all four comparisons are false): the output and the gradients of the
+    other points must be unaffected and the gated point's own gradients are zero.  The fast kernels used to
+    turn such a point into NaN through inf - inf in the fractional part."""
+    levels = [(12, 20), (6, 10), (3, 5), (2, 3)]
+    D = 32 if path == "fast" else 16                     # D != 32 -> generic kernels
+    inp = oracle.make_inputs("model", 2, levels, D=D, seed=14)
+    loc = inp["loc"].clone()
+    bad = torch.tensor([float("inf"), float("-inf"), float("nan"), 1e38, -1e38, 3.0e30])
+    flat = loc.view(-1, 2)
+    idx = torch.arange(0, flat.shape[0], 17)
+    flat[idx, 0] = bad[torch.arange(idx.numel()) % bad.numel()]
+    flat[idx[::2], 1] = bad[(torch.arange(idx[::2].numel()) + 2) % bad.numel()]
+    t = dev_inputs(dict(inp, loc=loc), torch.float32)
+    lib = capi.load()
+    sh = capi.shape_of(t["value"], t["loc"], len(levels))
+    assert (b"fast" in lib.msda_kernel_name(C.byref(sh), 0)) == (path == "fast")
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    gv, gl, ga = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    assert torch.isfinite(out).all() and torch.isfinite(gv).all() and torch.isfinite(ga).all()
+    # truth: the same call with the bad points moved far outside (finite), where every implementation gates them
+    good = loc.clone()
+    nf = ~torch.isfinite(good) | (good.abs() > 1e6)
+    good[nf] = 5.0
+    ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(inp["value"].double(), inp["shapes"], good.double(),
+                                                      inp["aw"].double(), inp["grad_out"].double())
+    assert oracle.max_rel(out.cpu(), ref_out) < FWD_TOL
+    assert oracle.max_rel(gv.cpu(), rv) < GRAD_TOL and oracle.max_rel(ga.cpu(), ra) < GRAD_TOL
+    bad_pt = nf.any(-1)
+    assert float(ga.cpu()[bad_pt].abs().max()) == 0.0
+    assert float(torch.nan_to_num(gl.cpu()[bad_pt], nan=1.0).abs().max()) == 0.0
+    ok = ~bad_pt
+    err = (gl.cpu()[ok].double() - rl[ok]).abs().max() / rl.abs().max()
+    assert float(err) < 1e-3          # boundary points excluded elsewhere; here only the blast radius matters

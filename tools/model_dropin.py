@@ -217,7 +217,10 @@ def synthetic_targets(n_clips, T, H, W, device, seed):
     return targets
 
 
-def main():
+def run(argv=None):
+    """Parse `argv` (None = sys.argv), run the configured workload and return the result line as a dict on
+    rank 0 (None on the other ranks; an int exit code for --stage).  bench.py --workload model3|model4 calls this
+    in-process under its own clock sampler."""
     ap = argparse.ArgumentParser()
     ap.add_argument("--stage", action="store_true")
     ap.add_argument("--config", type=int, default=3, choices=(3, 4))
@@ -243,7 +246,7 @@ def main():
     ap.add_argument("--compare", action="store_true",
                     help="after timing, run one more step on the OTHER operator in the same process (same weights, "
                          "same inputs) and report the largest relative difference of the model outputs")
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     if a.stage:
         return stage()
 
@@ -403,13 +406,20 @@ def main():
         "result_checksum": float(r.float().abs().mean()) if hasattr(r, "float") else None,
         "weights": "random init (seed 1234), synthetic clip", "dtype": "fp32" + (" (matmul TF32 allowed)" if a.tf32 else ""), "compare_max_rel": compare,
     }
-    if rank == 0:
-        print(json.dumps(line))
-        if a.out:
-            with open(a.out, "a") as f:
-                f.write(json.dumps(line) + "\n")
+    if rank == 0 and a.out:
+        with open(a.out, "a") as f:
+            f.write(json.dumps(line) + "\n")
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
+
+
+def main():
+    r = run()
+    if isinstance(r, int):
+        return r
+    if r is not None:
+        print(json.dumps(r))
     return 0
 
 
