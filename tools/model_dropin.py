@@ -243,6 +243,16 @@ def run(argv=None):
                     help="torch.backends.cuda.matmul.allow_tf32 = True (NOT the reference's setting; shows what bounds the "
                          "model outside the hot path: its nn.Linear layers run as fp32 SIMT GEMMs by default)")
     ap.add_argument("--profile", default=None, help="write a torch.profiler table of one extra step (top CUDA kernels) to this file")
+    ap.add_argument("--fused-topk", action="store_true",
+                    help="decoder loop with this repo's one-launch sample selection (decoder_sample_topk) in place of the five "
+                         "tensor ops of tce_deformable_transformer.py:752-758 (tools/decoder_topk_patch.py; no reference file is edited)")
+    ap.add_argument("--compare-topk", action="store_true",
+                    help="config 3: run the same clip through the reference's decoder loop and through the fused one and compare "
+                         "the model outputs and the kept samples bit for bit (attention-weight ties are broken by a seeded bias "
+                         "perturbation first: at initialisation ALL weights tie and torch.topk leaves that order unspecified)")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="config 3: capture the whole model forward in one CUDA graph and time replays (possible on this operator "
+                         "only: the reference's forward calls cudaDeviceSynchronize, ms_deform_im2col_cuda.cuh:1260)")
     ap.add_argument("--compare", action="store_true",
                     help="after timing, run one more step on the OTHER operator in the same process (same weights, "
                          "same inputs) and report the largest relative difference of the model outputs")
@@ -299,6 +309,11 @@ def run(argv=None):
                     # and the FTF layer binds but never reads them (:451-452)
                     m.return_sampling = ".cross_attn" in name
         assert n_fused > 0, "the reference transformer did not pick up the swapped module class"
+    topk_original = None
+    if a.fused_topk and not cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import decoder_topk_patch
+        topk_original = decoder_topk_patch.install()
     calls = count_op_calls()
     n_params = sum(p.numel() for p in model.parameters())
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
@@ -344,6 +359,30 @@ def run(argv=None):
             torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)                              # engine.py:77
             opt.step()
             return loss.detach()
+
+    graph_note = None
+    if a.cuda_graph and a.config == 3 and not cpu:
+        eager_step = step
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    eager_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = eager_step()
+
+            def step():
+                graph.replay()
+                return static_out
+            graph_note = "whole forward captured in one CUDA graph"
+        except Exception as exc:      # what blocks the capture is the result
+            step = eager_step
+            torch.cuda.synchronize()
+            graph_note = "capture failed: " + repr(exc)[:300]
 
     for _ in range(a.warmup):
         r = step()
@@ -395,6 +434,37 @@ def run(argv=None):
         for k in ("pred_logits", "pred_boxes", "pred_masks"):
             x, y = mine[k].double(), theirs[k].double()
             compare[k] = float((x - y).abs().max() / y.abs().max())
+    topk_compare = None
+    if a.compare_topk and not cpu and a.config == 3:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import decoder_topk_patch
+        if topk_original is not None:
+            decoder_topk_patch.uninstall(topk_original)
+        gen = torch.Generator(device="cpu").manual_seed(99)
+        n_mod = 0
+        for name, m in model.named_modules():
+            if hasattr(m, "attention_weights") and hasattr(m, "sampling_offsets"):
+                with torch.no_grad():
+                    m.attention_weights.bias.add_(torch.randn(m.attention_weights.bias.shape, generator=gen).to(device))
+                n_mod += 1
+        kept = {}
+        decoder = model.transformer.decoder
+        hook = decoder.register_forward_hook(lambda mod, inp, out: kept.__setitem__("s", out[2].detach().clone()))
+        with torch.no_grad():
+            ref_out = model([clip], captions, target)
+        ref_samples = kept["s"]
+        original = decoder_topk_patch.install()
+        with torch.no_grad():
+            new_out = model([clip], captions, target)
+        new_samples = kept["s"]
+        decoder_topk_patch.uninstall(original)
+        hook.remove()
+        topk_compare = {"modules_with_perturbed_weight_bias": n_mod,
+                        "kept_samples_shape": list(ref_samples.shape),
+                        "kept_samples_bit_identical": bool(torch.equal(ref_samples, new_samples)),
+                        "kept_samples_max_abs_diff": float((ref_samples - new_samples).abs().max())}
+        for k in ("pred_logits", "pred_boxes", "pred_masks"):
+            topk_compare[k + "_bit_identical"] = bool(torch.equal(ref_out[k], new_out[k]))
     line = {
         "what": f"BASELINE.json configs[{a.config - 1}]: unmodified reference model on the {a.op} operator",
         "op_extension": ext_name, "module_class": a.module + ("+fused" if a.fused else ""), "config": a.config, "backbone": backbone, "enc_dec_layers": layers,
@@ -405,6 +475,8 @@ def run(argv=None):
         "b200_kernel_launches_per_step": b200_launches, "params_M": n_params / 1e6, "trainable_params_M": n_train / 1e6,
         "result_checksum": float(r.float().abs().mean()) if hasattr(r, "float") else None,
         "weights": "random init (seed 1234), synthetic clip", "dtype": "fp32" + (" (matmul TF32 allowed)" if a.tf32 else ""), "compare_max_rel": compare,
+        "decoder_topk": "fused (decoder_sample_topk)" if a.fused_topk else "reference loop", "decoder_topk_compare": topk_compare,
+        "cuda_graph": graph_note,
     }
     if rank == 0 and a.out:
         with open(a.out, "a") as f:
