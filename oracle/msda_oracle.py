@@ -206,6 +206,19 @@ def max_rel(a, ref):
     return float(((a - ref).abs().max() / scale))
 
 
+def assert_close(a, ref, tol, what=""):
+    """The parity criterion of this repo, written out: the error of EVERY element is held against the tensor's scale,
+    |a - ref| <= tol * max|ref|  (= max_rel(a, ref) <= tol), which is also torch.allclose(a, ref, rtol=tol,
+    atol=tol * max|ref|) — asserted as well so that the elementwise form is on record.  A purely elementwise relative
+    bound is meaningless for this operator: outputs and gradients are signed sums that cancel to ~0 for some elements."""
+    a, ref = torch.as_tensor(a).double(), torch.as_tensor(ref).double()
+    scale = float(ref.abs().max().clamp_min(1e-300))
+    err = float((a - ref).abs().max()) / scale
+    assert err <= tol, (what, "max|a-b|/max|b|", err, "tol", tol)
+    assert torch.allclose(a, ref, rtol=tol, atol=tol * scale), (what, "allclose(rtol=tol, atol=tol*scale)")
+    return err
+
+
 def rel_l2(a, ref):
     a, ref = torch.as_tensor(a).double(), torch.as_tensor(ref).double()
     return float((a - ref).norm() / ref.norm().clamp_min(1e-300))

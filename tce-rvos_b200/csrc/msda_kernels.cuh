@@ -167,6 +167,12 @@ template <> struct VecIOn<float, 4> {
         const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
+    // corner rows of the coarse levels: every query of the frame reads them, keep them in L1 (timing experiment)
+    static __device__ __forceinline__ void load_keep(const float *p, float (&v)[4])
+    {
+        asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+    }
     static __device__ __forceinline__ void zero(float (&v)[4]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
     static __device__ __forceinline__ void load_stream(const float *p, float (&v)[4])
     {
@@ -585,6 +591,17 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 #else
 #pragma unroll
             for (int k = 0; k < 4; ++k) VecIO<VT>::zero(v[b][k]);
+#if MSDA_EXP == 30 || MSDA_EXP == 31
+            if constexpr (sizeof(VT) == 4) {
+                if ((p >> 2) >= (MSDA_EXP == 30 ? 2 : 1)) {
+                    if (pv[b].mask & 1) VecIOn<float, 4>::load_keep(reinterpret_cast<const float *>(r0), v[b][0]);
+                    if (pv[b].mask & 2) VecIOn<float, 4>::load_keep(reinterpret_cast<const float *>(r0 + pixb), v[b][1]);
+                    if (pv[b].mask & 4) VecIOn<float, 4>::load_keep(reinterpret_cast<const float *>(r1), v[b][2]);
+                    if (pv[b].mask & 8) VecIOn<float, 4>::load_keep(reinterpret_cast<const float *>(r1 + pixb), v[b][3]);
+                    continue;
+                }
+            }
+#endif
             if (pv[b].mask & 1) VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v[b][0]);
             if (pv[b].mask & 2) VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v[b][1]);
             if (pv[b].mask & 4) VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v[b][2]);
