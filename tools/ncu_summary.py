@@ -63,7 +63,7 @@ def main():
     if os.path.exists(launches):
         rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
         hdr = rows[0]
-        first_n = int(os.environ.get("FIRST_N", "46"))   # (warm-up + steps) x 2 kernels of the device-timed loop
+        first_n = int(os.environ.get("FIRST_N", "110"))   # (warm-up + steps) x 2 kernels of the device-timed loop
         rows = rows[: 1 + first_n]
         ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
         per = OrderedDict()
@@ -74,11 +74,13 @@ def main():
                 pass
         total = sum(sum(v) for v in per.values())
         with open(os.path.join(PROF, f"{tag}_launches_summary.md"), "w") as f:
-            f.write(f"# {tag}: ncu launch list of `python bench.py --steps 20 --warmup 3 --no-cpu-baseline`\n\n")
+            cmd = os.environ.get("BENCH_CMD", "python bench.py --steps 20 --warmup 5 --no-cpu-baseline")
+            f.write(f"# {tag}: ncu launch list of `{cmd}`\n\n")
             f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` (per-launch times are cold-cache and "
-                    "serialised: compare SHARES).  Only the launches of the device-timed loop (3 warm-up + 20 steps, 2 kernels per step; the "
-                    "grad_value zero-fill is a cudaMemsetAsync, not a kernel) are listed; the e2e leg that follows launches the "
-                    "same two kernels once per frame (10 chunks per step).  Full list: `" + f"{tag}_launches.csv`.\n\n")
+                    f"serialised: compare SHARES).  The first {first_n} launches are summarised: the warm-up steps, the CUDA-graph "
+                    "replays of the timed region (ncu profiles the kernel nodes of a replayed graph one by one) and the instrumented "
+                    "eager re-run, 2 kernels per step (the grad_value zero-fill is a cudaMemsetAsync, not a kernel); the post-roll "
+                    "and the e2e leg that follow launch the same two kernels.  Full list: `" + f"{tag}_launches.csv`.\n\n")
             f.write("| kernel | launches | mean us | share of captured GPU time |\n|---|---|---|---|\n")
             for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
                 f.write(f"| `{k[:110]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {100 * sum(v) / total:.1f}% |\n")
