@@ -67,6 +67,8 @@ inline bool fast_eligible(const Dims &d)
     if (d.D != msda::kFastD || d.L * d.P != msda::kFastLP) return false;
     // offsets inside one frame are 32-bit byte offsets (also for the fp32 scratch of bf16 grads)
     if (d.S * d.M * d.D * 4 >= (int64_t(1) << 31)) return false;
+    // a point travels between lanes as (pixel index << 8 | corner masks) in one 32-bit word
+    if (d.S >= (int64_t(1) << 22)) return false;
     if (d.vdt == MSDA_F32 && d.ldt == MSDA_F32) return d.M % 4 == 0;
     if (d.vdt == MSDA_BF16 && (d.ldt == MSDA_F32 || d.ldt == MSDA_BF16)) return d.M % 8 == 0;
     return false;

@@ -14,7 +14,7 @@
 //    LDG.128 fetches the same corner for HPW heads (fp32: 4 heads x 128 B, bf16: 8 heads x 64 B).
 //    The per-point work (coordinate scaling, floor, bounds masks, bilinear weights) is done ONCE
 //    by the lane that loaded the point (coalesced 16-byte loads of sampling_loc/attn_weight) and
-//    broadcast inside the LPH-lane group with 6 shuffles; the reference redoes it in all
+//    broadcast inside the LPH-lane group with 4 (forward) / 5 (backward) shuffles; the reference redoes it in all
 //    32 channel threads.
 //  * BACKWARD: grad_value goes out as 16-byte vector reductions (red.global.add.v4.f32 — one
 //    instruction per lane per corner instead of 4 scalar atomics); the channel dot products
@@ -148,9 +148,9 @@ template <> struct FastCfg<__nv_bfloat16> {
 #ifndef MSDA_FWD_BATCH
 #define MSDA_FWD_BATCH 2
 #endif
-#ifndef MSDA_TABLE
-#define MSDA_TABLE 0   // 1: a point's weights reach the other lanes of its head through a per-warp table in
-                       // shared memory (one broadcast LDS.128 per point); 0: four shuffles per point
+#ifndef MSDA_MERGE
+#define MSDA_MERGE 1   // 1: backward: corners of the points of one (query, head, level) that fall on the same pixel are
+                       // merged by the lanes that own the points before anything is broadcast (TCE geometry only)
 #endif
 #ifndef MSDA_EXP
 #define MSDA_EXP 0     // timing experiments only (tools/variants.py); 0 = product
@@ -166,12 +166,6 @@ template <> struct VecIOn<float, 4> {
     {
         const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-    // corner rows of the coarse levels: every query of the frame reads them, keep them in L1 (timing experiment)
-    static __device__ __forceinline__ void load_keep(const float *p, float (&v)[4])
-    {
-        asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
     }
     static __device__ __forceinline__ void zero(float (&v)[4]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
     static __device__ __forceinline__ void load_stream(const float *p, float (&v)[4])
@@ -387,23 +381,96 @@ __device__ __forceinline__ PointView view_point(const OwnedPoint &o, int src)
     return v;
 }
 
-// The same hand-over through shared memory: the owner lane stores (ta, tb, lw, packed) of its points once
-// (16 bytes each), every lane of the head reads a point back with ONE broadcast LDS.128 — 4 different
-// addresses per warp = one wavefront of the L1TEX data pipe instead of four SHFL passes (the pipe is what
-// bounds both fast kernels).  Table layout: [point][head of the warp].
-__device__ __forceinline__ void table_put(float4 *table, int slot, const OwnedPoint &o)
+// --------------------------------------------------------------------------------------------
+// Merging the duplicate corners of one (query, head, level).
+//
+// The P points a head samples on one level are close to each other (the module initialises them 1, 2, 3, 4 px
+// along one direction, ms_deform_attn.py:63-71), so the 2x2 corner blocks of consecutive points overlap: on
+// the benchmark's model-like inputs 22 % of all (point, corner) pairs hit a pixel that the previous point of
+// the same level already touches (1.4 % for uniform random locations; profiles/r02_merge.md).  Every such pair
+// is a 128-byte line reduced twice by the backward, and the backward is bound by exactly that number
+// (DESIGN.md section 4).  All contributions of one (query, head) carry the same grad_out, so merging is scalar
+// work: the duplicate corner's weight is ADDED to the first occurrence's and the duplicate is switched off.
+// It is done once per point by the lane that owns the point, in a chain from the last point of the level to
+// the first (D -> C -> B -> A), so that a pixel shared by three points ends up in one slot.  BACKWARD ONLY:
+// in the forward a duplicate corner is a load that hits the line its twin has just brought into L1, the
+// cheapest access there is, and the extra hand-over word costs more than it saves (measured: 170 -> 177 us).
+//
+// A merged point travels to the other lanes of the head as its four corner weights (no longer separable into
+// (ta, tb) x (hw, lw)) and one word: base << 8 | load mask << 4 | active mask.  `load mask` = corners whose
+// value row is read (the backward needs every corner's dot product, merged or not), `active mask` = corners
+// that are reduced into grad_value.
+// --------------------------------------------------------------------------------------------
+struct MergedPoint {
+    float w[4];
+    int packed;        // base << 8 | load mask << 4 | active mask
+    __device__ __forceinline__ int base() const { return packed >> 8; }
+    __device__ __forceinline__ int lmask() const { return (packed >> 4) & 15; }
+    __device__ __forceinline__ int amask() const { return packed & 15; }
+};
+
+__device__ __forceinline__ MergedPoint merged_from(const OwnedPoint &o)
 {
-    table[slot] = make_float4(o.ta, o.tb, o.lw, __int_as_float(o.packed));
+    MergedPoint m;
+    const float hw = 1.f - o.lw;
+    m.w[0] = o.ta * hw; m.w[1] = o.ta * o.lw; m.w[2] = o.tb * hw; m.w[3] = o.tb * o.lw;
+    const int mask = o.packed & 15;
+    m.packed = ((o.packed >> 4) << 8) | (mask << 4) | mask;
+    return m;
 }
-__device__ __forceinline__ PointView table_view(const float4 *table, int slot)
+
+// Fold the corners of point b that coincide with an active corner of the point at (base_a, mask_a) into wa[] and
+// switch them off in b.  Two active corners have the same pixel index only if they are the same pixel (both are
+// inside the level).  `commit` = false makes the call a no-op (lanes that only take part in the exchange).
+__device__ __forceinline__ void fold_into(float (&wa)[4], int mask_a, int base_a, MergedPoint &b, int W, bool commit)
 {
-    const float4 d = table[slot];
-    const float hw = 1.f - d.z;
-    PointView v;
-    v.w0 = d.x * hw; v.w1 = d.x * d.z; v.w2 = d.y * hw; v.w3 = d.y * d.z;
-    const int packed = __float_as_int(d.w);
-    v.base = packed >> 4;
-    v.mask = packed & 15;
+    const int d = b.base() - base_a;
+    const int off[4] = {0, 1, W, W + 1};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool hit = commit && (d + off[c] == off[k]) && ((b.packed >> c) & 1) && ((mask_a >> k) & 1);
+            wa[k] += hit ? b.w[c] : 0.f;
+            b.packed = hit ? (b.packed & ~(1 << c)) : b.packed;
+        }
+    }
+}
+
+// All points a lane owns lie on one level (TCE geometry: P = 4; PPL = 2 -> the level's points are split over the
+// lane pair (2l, 2l+1), PPL = 4 -> one lane owns the whole level).
+template <int PPL, int LPH>
+__device__ __forceinline__ void merge_level(MergedPoint (&m)[PPL], int W, int j)
+{
+    if constexpr (PPL == 4) {
+        fold_into(m[2].w, m[2].amask(), m[2].base(), m[3], W, true);
+        fold_into(m[1].w, m[1].amask(), m[1].base(), m[2], W, true);
+        fold_into(m[0].w, m[0].amask(), m[0].base(), m[1], W, true);
+    } else {
+        static_assert(PPL == 2, "lanes own 2 or 4 points");
+        const bool odd = (j & 1) != 0;
+        fold_into(m[0].w, m[0].amask(), m[0].base(), m[1], W, odd);             // D -> C on the odd lane
+        // C -> B: B is the even lane's second point.  The odd lane gets B's position, works out what C adds to
+        // each corner of B, and sends the four sums back.
+        const int pb = __shfl_xor_sync(kFull, m[1].packed, 1, LPH);
+        float add[4] = {0.f, 0.f, 0.f, 0.f};
+        fold_into(add, pb & 15, pb >> 8, m[0], W, odd);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float r = __shfl_xor_sync(kFull, add[k], 1, LPH);
+            m[1].w[k] += odd ? 0.f : r;
+        }
+        fold_into(m[0].w, m[0].amask(), m[0].base(), m[1], W, !odd);            // B -> A on the even lane
+    }
+}
+
+template <int LPH>
+__device__ __forceinline__ MergedPoint view_merged(const MergedPoint &m, int src)
+{
+    MergedPoint v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v.w[k] = __shfl_sync(kFull, m.w[k], src, LPH);
+    v.packed = __shfl_sync(kFull, m.packed, src, LPH);
     return v;
 }
 
@@ -537,14 +604,6 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 #pragma unroll
     for (int pp = 0; pp < PPL; ++pp)
         own[pp] = own_point(xy[2 * pp], xy[2 * pp + 1], a[pp], Hs[pp], Ws[pp], starts[pp]);
-#if MSDA_TABLE
-    __shared__ float4 point_table[8][kFastLP * HPW];
-    float4 *table = point_table[threadIdx.x >> 5];
-#pragma unroll
-    for (int pp = 0; pp < PPL; ++pp) table_put(table, (j * PPL + pp) * HPW + g, own[pp]);
-    __syncwarp();
-#endif
-
     // All offsets inside a frame are 32-bit byte offsets.
     const int pix = M * kFastD;                            // elements between neighbouring pixels
     const int pixb = pix * static_cast<int>(sizeof(VT));   // bytes
@@ -569,44 +628,16 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const int p = p0 + b, src = p / PPL, pp = p % PPL;
-#if MSDA_EXP == 4
-            pv[b].w0 = own[pp].ta; pv[b].w1 = own[pp].tb; pv[b].w2 = own[pp].lw; pv[b].w3 = own[pp].lw;
-            pv[b].base = own[pp].packed >> 4; pv[b].mask = own[pp].packed & 15;
-#elif MSDA_TABLE
-            pv[b] = table_view(table, p * HPW + g);
-#else
             pv[b] = view_point<LPH>(own[pp], src);
-#endif
-#if MSDA_EXP == 5
-            pv[b].base &= 63;
-#endif
             const int rb = TCE ? rowb[p >> 2] : __shfl_sync(kFull, own[pp].W, src, LPH) * pixb;
             const char *r0 = vlane + static_cast<int64_t>(pv[b].base) * pixb;
             const char *r1 = r0 + rb;
-#if MSDA_EXP == 1
-            VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v[b][0]);
-            VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v[b][1]);
-            VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v[b][2]);
-            VecIO<VT>::load(reinterpret_cast<const VT *>(r1 + pixb), v[b][3]);
-#else
 #pragma unroll
             for (int k = 0; k < 4; ++k) VecIO<VT>::zero(v[b][k]);
-#if MSDA_EXP == 30 || MSDA_EXP == 31
-            if constexpr (sizeof(VT) == 4) {
-                if ((p >> 2) >= (MSDA_EXP == 30 ? 2 : 1)) {
-                    if (pv[b].mask & 1) VecIOn<float, 4>::load_keep(reinterpret_cast<const float *>(r0), v[b][0]);
-                    if (pv[b].mask & 2) VecIOn<float, 4>::load_keep(reinterpret_cast<const float *>(r0 + pixb), v[b][1]);
-                    if (pv[b].mask & 4) VecIOn<float, 4>::load_keep(reinterpret_cast<const float *>(r1), v[b][2]);
-                    if (pv[b].mask & 8) VecIOn<float, 4>::load_keep(reinterpret_cast<const float *>(r1 + pixb), v[b][3]);
-                    continue;
-                }
-            }
-#endif
             if (pv[b].mask & 1) VecIO<VT>::load(reinterpret_cast<const VT *>(r0), v[b][0]);
             if (pv[b].mask & 2) VecIO<VT>::load(reinterpret_cast<const VT *>(r0 + pixb), v[b][1]);
             if (pv[b].mask & 4) VecIO<VT>::load(reinterpret_cast<const VT *>(r1), v[b][2]);
             if (pv[b].mask & 8) VecIO<VT>::load(reinterpret_cast<const VT *>(r1 + pixb), v[b][3]);
-#endif
         }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -746,12 +777,11 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 #pragma unroll
     for (int pp = 0; pp < PPL; ++pp)
         own[pp] = own_point(xy[2 * pp], xy[2 * pp + 1], a[pp], Hs[pp], Ws[pp], starts[pp]);
-#if MSDA_TABLE
-    __shared__ float4 point_table[8][kFastLP * HPW];
-    float4 *table = point_table[threadIdx.x >> 5];
+    MergedPoint mp[PPL];
 #pragma unroll
-    for (int pp = 0; pp < PPL; ++pp) table_put(table, (j * PPL + pp) * HPW + g, own[pp]);
-    __syncwarp();
+    for (int pp = 0; pp < PPL; ++pp) mp[pp] = merged_from(own[pp]);
+#if MSDA_MERGE
+    if (TCE) merge_level<PPL, LPH>(mp, Ws[0], j);
 #endif
 
     const int pix = M * kFastD;
@@ -770,15 +800,11 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     auto leaf = [&](auto pc, float (&d)[4]) {
         constexpr int p = decltype(pc)::value;
         constexpr int src = p / PPL, pp = p % PPL;
-#if MSDA_TABLE
-        const PointView pv = table_view(table, p * HPW + g);
-#else
-        const PointView pv = view_point<LPH>(own[pp], src);
-#endif
+        const MergedPoint pv = view_merged<LPH>(mp[pp], src);
         const int W = TCE ? rowW[p >> 2] : __shfl_sync(kFull, own[pp].W, src, LPH);
-        const char *r0 = vlane + static_cast<int64_t>(pv.base) * pixb;
+        const char *r0 = vlane + static_cast<int64_t>(pv.base()) * pixb;
         const char *r1 = r0 + static_cast<int64_t>(W) * pixb;
-        char *g0 = glane + static_cast<int64_t>(pv.base) * gpixb;
+        char *g0 = glane + static_cast<int64_t>(pv.base()) * gpixb;
         char *g1 = g0 + static_cast<int64_t>(W) * gpixb;
         float v0[CPL], v1[CPL], v2[CPL], v3[CPL];
         IO::zero(v0); IO::zero(v1); IO::zero(v2); IO::zero(v3);
@@ -799,19 +825,21 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
         constexpr bool kReds = true;
 #endif
         if (kLoads) {
-            if (pv.mask & 1) IO::load(reinterpret_cast<const VT *>(r0), v0);
-            if (pv.mask & 2) IO::load(reinterpret_cast<const VT *>(r0 + pixb), v1);
-            if (pv.mask & 4) IO::load(reinterpret_cast<const VT *>(r1), v2);
-            if (pv.mask & 8) IO::load(reinterpret_cast<const VT *>(r1 + pixb), v3);
+            // every corner's row is read (its dot product feeds the point's own gradients) ...
+            if (pv.lmask() & 1) IO::load(reinterpret_cast<const VT *>(r0), v0);
+            if (pv.lmask() & 2) IO::load(reinterpret_cast<const VT *>(r0 + pixb), v1);
+            if (pv.lmask() & 4) IO::load(reinterpret_cast<const VT *>(r1), v2);
+            if (pv.lmask() & 8) IO::load(reinterpret_cast<const VT *>(r1 + pixb), v3);
         } else {
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) { v0[c] = pv.w0; v1[c] = pv.w1; v2[c] = pv.w2; v3[c] = pv.w3; }
+            for (int c = 0; c < CPL; ++c) { v0[c] = pv.w[0]; v1[c] = pv.w[1]; v2[c] = pv.w[2]; v3[c] = pv.w[3]; }
         }
         if (kReds) {
-            GradScatter<VT, GT, CPL>::add(pv.mask & 1, g0, pv.w0, go);
-            GradScatter<VT, GT, CPL>::add(pv.mask & 2, g0 + gpixb, pv.w1, go);
-            GradScatter<VT, GT, CPL>::add(pv.mask & 4, g1, pv.w2, go);
-            GradScatter<VT, GT, CPL>::add(pv.mask & 8, g1 + gpixb, pv.w3, go);
+            // ... but a pixel shared with an earlier point of the level is reduced once, with the summed weight
+            GradScatter<VT, GT, CPL>::add(pv.amask() & 1, g0, pv.w[0], go);
+            GradScatter<VT, GT, CPL>::add(pv.amask() & 2, g0 + gpixb, pv.w[1], go);
+            GradScatter<VT, GT, CPL>::add(pv.amask() & 4, g1, pv.w[2], go);
+            GradScatter<VT, GT, CPL>::add(pv.amask() & 8, g1 + gpixb, pv.w[3], go);
         }
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll

@@ -758,3 +758,48 @@ def test_non_finite_and_overflowing_locations_contribute_nothing(capi, oracle, p
     ok = ~bad_pt
     err = (gl.cpu()[ok].double() - rl[ok]).abs().max() / rl.abs().max()
     assert float(err) < 1e-3          # boundary points excluded elsewhere; here only the blast radius matters
+
+
+# ------------------------------------------------------------------------------------------------
+# merging of the duplicate corners of one (query, head, level)  (msda_kernels.cuh: merge_level)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,loc_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
+                                             (torch.bfloat16, torch.bfloat16)])
+def test_overlapping_points_within_a_level(capi, oracle, dtype, loc_dtype):
+    """The fast kernels merge the corners that several points of one (query, head, level) share before they load /
+    reduce them.  Drive every overlap pattern on purpose: the four points of a level are placed on a small integer
+    lattice around the reference point (offsets 0, +-1 px in x and y, in every order, so that blocks coincide, overlap
+    by a column, by a row, by one diagonal corner, or not at all), including queries at the borders (corners dropped
+    by zero padding), points outside the map (gated off) between two overlapping ones, and zero attention weights."""
+    levels = [(12, 20), (6, 10), (5, 1), (2, 3)]           # a level of width 1: pixel offsets 1 and W alias as indices
+    g = torch.Generator().manual_seed(31)
+    N, M, P, L = 3, 8, 4, 4
+    S = sum(h * w for h, w in levels)
+    inp = oracle.make_inputs("model", N, levels, seed=31)
+    Lq = inp["loc"].shape[1]
+    ref = oracle.reference_points_grid(levels)                                   # [S, 2], pixel centres
+    wh = torch.tensor([[w, h] for h, w in levels], dtype=torch.float32)
+    step = torch.randint(-1, 2, (N, Lq, M, L, P, 2), generator=g).float()        # lattice offsets in pixels
+    frac = 0.25 + 0.5 * torch.rand(N, Lq, M, L, 1, 2, generator=g)               # same sub-pixel phase for the 4 points
+    loc = ref[None, :, None, None, None, :] + (step + frac - 0.5) / wh[None, None, None, :, None, :]
+    far = torch.rand(N, Lq, M, L, P, generator=g) < 0.1                          # some points far outside
+    loc[far] = 3.0
+    aw = inp["aw"].clone()
+    aw[torch.rand(aw.shape, generator=g) < 0.1] = 0.0
+    src = dict(inp, loc=loc.contiguous(), aw=aw.contiguous())
+    t = dev_inputs(src, dtype, loc_dtype)
+    lib = capi.load()
+    sh = capi.shape_of(t["value"], t["loc"], L)
+    assert b"fast" in lib.msda_kernel_name(C.byref(sh), 0)
+    out = capi.forward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"])
+    got = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"])
+    ref_out, rv, rl, ra = oracle.core_pytorch_fwd_bwd(t["value"].cpu().double(), inp["shapes"], t["loc"].cpu().double(),
+                                                      t["aw"].cpu().double(), t["grad_out"].cpu().double())
+    f_tol, g_tol = (FWD_TOL, GRAD_TOL) if dtype == torch.float32 else (BF16_TOL, BF16_TOL)
+    assert oracle.max_rel(out.float().cpu(), ref_out) < f_tol
+    eps = 1e-4 if loc_dtype == torch.float32 else 2e-2
+    check_grads(oracle, tuple(x.float() for x in got), (rv, rl, ra), t["loc"].float().cpu(), levels, g_tol, eps_px=eps, stress=True)
+    if dtype == torch.bfloat16:      # the direct 16-bit reduction path (4 lanes x 8 channels, one lane owns a whole level)
+        gv2, gl2, ga2 = capi.backward(t["value"], t["shapes"], t["lsi"], t["loc"], t["aw"], t["grad_out"], use_workspace=False)
+        assert oracle.max_rel(gv2.float().cpu(), rv) < 1.5e-1
+        assert oracle.max_rel(ga2.float().cpu(), ra) < BF16_TOL
