@@ -253,20 +253,28 @@ def run_reference(args, wl, rank):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def count_line_updates(loc, levels):
-    """Number of 128-byte grad_value line updates one backward issues: one per (query, head, point, corner)
-    whose corner lies inside its level (the reference's gating, ms_deform_im2col_cuda.cuh:441 and :57-79)."""
+    """(issued, unmerged): the number of 128-byte grad_value line updates one backward issues and the number the
+    operator's definition asks for.  Unmerged: one per (query, head, point, corner) whose corner lies inside its level
+    (the reference's gating, ms_deform_im2col_cuda.cuh:441 and :57-79).  Issued: the backward kernel folds a corner
+    that falls on a pixel the PREVIOUS point of the same (query, head, level) also touches into that point's reduction
+    (msda_kernels.cuh merge_level), so those are not sent."""
     import torch
-    total = 0
+    total = dup = 0
     for l, (H, W) in enumerate(levels):
         x = loc[:, :, :, l, :, 0] * W - 0.5
         y = loc[:, :, :, l, :, 1] * H - 0.5
         inside = (x > -1) & (y > -1) & (x < W) & (y < H)
-        x0, y0 = torch.floor(x), torch.floor(y)
+        x0, y0 = torch.floor(x).long(), torch.floor(y).long()
+        ids = []
         for dy in (0, 1):
             for dx in (0, 1):
                 ok = inside & (x0 + dx >= 0) & (x0 + dx <= W - 1) & (y0 + dy >= 0) & (y0 + dy <= H - 1)
-                total += int(ok.sum())
-    return total
+                ids.append(torch.where(ok, (y0 + dy) * W + (x0 + dx), torch.full_like(x0, -1)))
+        ids = torch.stack(ids, -1)                                        # [N, Lq, M, P, 4] pixel index or -1
+        total += int((ids >= 0).sum())
+        cur, prev = ids[:, :, :, 1:, :, None], ids[:, :, :, :-1, None, :]
+        dup += int(((cur >= 0) & (cur == prev)).any(-1).sum())
+    return total - dup, total
 
 
 # measured on this pool (profiles/r01_microbench_bulk_red.txt, gpurun_out/red_scaling.log): the chip sustains 47.5-49.4 G
@@ -348,7 +356,8 @@ def run_ours(args, wl, rank, local_rank, world):
                          aw=grow(inp["aw"].to(dev)).requires_grad_(True), go=grow(inp["grad_out"].to(dev, tdt))))
     shapes, lsi = inp["shapes"].to(dev), inp["lsi"].to(dev)
     host_set = inp                                                  # last set, for the e2e leg and the shard check
-    line_updates = count_line_updates(inp["loc"], wl.levels) * (N / wl.base_frames)
+    issued, unmerged = count_line_updates(inp["loc"], wl.levels)
+    line_updates, line_updates_unmerged = issued * (N / wl.base_frames), unmerged * (N / wl.base_frames)
     qh_per_step = N * Lq * M
     fn = pkg.MSDeformAttnFunction.apply
 
@@ -525,12 +534,14 @@ def run_ours(args, wl, rank, local_rank, world):
                            "fwd+bwd": {"us": step_us, "GB/s": (bytes_fwd + bytes_bwd) / step_us / 1e3,
                                        "frac": (bytes_fwd + bytes_bwd) / step_us / 1e3 / peak}}}
     # the unit that binds the backward (profiles/r02_bwd_split.md): the L2's reduction throughput — with the corner loads
-    # removed the pass still takes 93 % of its time, with the reductions removed 46 %
+    # removed the (unmerged) pass still takes 93 % of its time, with the reductions removed 46 %; the kernel therefore
+    # merges the duplicate corners of consecutive points before reducing them (profiles/r02_merge.md)
     roofline["l2_reduction"] = {
         "what": "backward pass: 128-byte grad_value line updates (red.global.add.v4.f32) per second against the rate the chip's L2 "
                 "sustains in a microbenchmark on this pool from 74 SMs upwards (profiles/r01_microbench_bulk_red.txt); "
                 "split experiment: profiles/r02_bwd_split.md",
-        "line_updates_per_launch": line_updates, "achieved_Glines_s": line_updates / (b_us * 1e-6) / 1e9,
+        "line_updates_per_launch": line_updates, "line_updates_before_merging": line_updates_unmerged,
+        "achieved_Glines_s": line_updates / (b_us * 1e-6) / 1e9,
         "peak_Glines_s": L2_REDUCTION_PEAK_GLINES, "frac": line_updates / (b_us * 1e-6) / 1e9 / L2_REDUCTION_PEAK_GLINES,
         "payload_TB_s": line_updates * 128 / (b_us * 1e-6) / 1e12}
     traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
