@@ -35,7 +35,7 @@ Keys of the line (config2 / sweep):
 * `cpu_baseline` / `--impl reference`: the reference's own ms_deform_attn_core_pytorch + autograd
                (models/ops/functions/ms_deform_attn_func.py:67-87; the staged file when present = kind
                "reference", else the oracle's restatement = kind "port") on a FIXED sample — one frame, all
-               queries, all host threads the process may use — so that the figure is reproducible.
+               queries, min(16, allowed cores) host threads — so that the figure is reproducible across boxes.
 
 Frames shard across ranks with no collective (weak scaling: every rank owns `frames_per_gpu` frames).
 """
@@ -196,13 +196,20 @@ def reference_cpu_function():
     return O.core_pytorch, "port"
 
 
+CPU_ARM_THREADS = 16      # fixed, so that the CPU figure (and the driver's GPU/CPU ratio) is the same on every box of the pool
+
+
 def host_threads():
-    """torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core the process is allowed."""
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm always uses min(16, cores the process is allowed) threads: the
+    1-GPU boxes of this pool expose 16 cores and the 8-GPU boxes 32, and grid_sample's backward gains only ~10 % from the
+    second 16, so a fixed count keeps the figure comparable between the two (verdict r1: the ratio swung 2x between
+    BENCH and SCALE with the sample and the thread count both floating)."""
     import torch
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
+    n = max(1, min(n, CPU_ARM_THREADS))
     if torch.get_num_threads() != n:
         torch.set_num_threads(n)
     return torch.get_num_threads()
