@@ -17,7 +17,9 @@
 //    broadcast inside the LPH-lane group with 4 (forward) / 5 (backward) shuffles; the reference redoes it in all
 //    32 channel threads.
 //  * BACKWARD: grad_value goes out as 16-byte vector reductions (red.global.add.v4.f32 — one
-//    instruction per lane per corner instead of 4 scalar atomics); the channel dot products
+//    instruction per lane per corner instead of 4 scalar atomics), after the corners that
+//    consecutive points of one (query, head, level) share have been merged by the lanes that own
+//    the points (the pass is bound by the number of line updates reaching the L2); the channel dot products
 //    needed by grad_attn_weight / grad_sampling_loc are reduced across the LPH lanes with a
 //    transposing butterfly (log2(LPH) exchange rounds that halve the live set each round) that
 //    ends with every lane holding exactly the points it loaded, so the two gradients are written
