@@ -3,7 +3,7 @@
 // a red.global.add.v4.f32?  The backward scatter of MSDA is bound by the rate of line updates
 // (DESIGN.md section 4), so this decides whether staging w*grad_out rows in shared memory pays.
 // Developer tool; not part of the product.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o bulk_red bulk_red.cu && ./bulk_red
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 --cudart shared -o bulk_red bulk_red.cu && ./bulk_red
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>

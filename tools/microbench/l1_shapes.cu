@@ -1,6 +1,6 @@
 // Microbenchmark: L1TEX throughput on B200 for the load/shuffle/reduction shapes the MSDA kernels
 // can be built from.  Developer tool (results recorded in DESIGN.md); not part of the product.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o l1_shapes l1_shapes.cu && ./l1_shapes
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 --cudart shared -o l1_shapes l1_shapes.cu && ./l1_shapes
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>

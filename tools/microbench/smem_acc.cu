@@ -3,7 +3,7 @@
 // Access shape of the kernel: a warp instruction carries 4 rows (one per 8-lane group), each lane
 // 16 bytes.  sm_100a has no native shared fp32 add (atomicAdd(float) = ATOMS.CAST.SPIN loop), so
 // the candidates are compare-and-swap loops of 32, 64 or 128 bits per lane.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o smem_acc smem_acc.cu && ./smem_acc
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 --cudart shared -o smem_acc smem_acc.cu && ./smem_acc
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
