@@ -86,6 +86,14 @@ inline unsigned grid_for_warps(int64_t warps, int threads)
     return static_cast<unsigned>((warps + wpb - 1) / wpb);
 }
 
+// grid of the fast kernels: with the query-major item map (MSDA_QMAP_*) the queries are padded to whole CTAs per head group
+inline unsigned grid_for_items(int64_t queries, int groups, int threads, bool qmap)
+{
+    const int64_t wpb = threads / 32;
+    if (!qmap) return grid_for_warps(queries * groups, threads);
+    return static_cast<unsigned>(((queries + wpb - 1) / wpb) * groups);
+}
+
 int sm_count_aux()
 {
     static int sms = 0;
@@ -118,7 +126,7 @@ int launch_fwd_fast(const Dims &d, const void *value, const int64_t *shapes, con
     if (items == 0) return MSDA_OK;
     constexpr int threads = 256;
     auto kern = (d.M == 8 && d.P == 4) ? msda::fwd_fast_kernel<VT, LT, PRO, true> : msda::fwd_fast_kernel<VT, LT, PRO, false>;
-    kern<<<grid_for_warps(items, threads), threads, 0, st>>>(
+    kern<<<grid_for_items(d.N * d.Lq, d.M / HPW, threads, MSDA_QMAP_FWD != 0), threads, 0, st>>>(
         static_cast<const VT *>(value), shapes, lsi, static_cast<const LT *>(loc),
         static_cast<const LT *>(aw), static_cast<VT *>(out), items, d.Lq, d.S, d.M, ilog2_exact(d.P), pro);
     ++g_launches;
@@ -207,7 +215,7 @@ int launch_bwd_fast(const Dims &d, const void *value, const int64_t *shapes, con
     if (items == 0) return MSDA_OK;
     constexpr int threads = 256;
     auto kern = (d.M == 8 && d.P == 4) ? msda::bwd_fast_kernel<VT, LT, GT, PRO, true> : msda::bwd_fast_kernel<VT, LT, GT, PRO, false>;
-    kern<<<grid_for_warps(items, threads), threads, 0, st>>>(
+    kern<<<grid_for_items(d.N * d.Lq, d.M / HPW, threads, MSDA_QMAP_BWD != 0), threads, 0, st>>>(
         static_cast<const VT *>(value), shapes, lsi, static_cast<const LT *>(loc),
         static_cast<const LT *>(aw), static_cast<const VT *>(go), gv, static_cast<LT *>(gl),
         static_cast<LT *>(ga), items, d.Lq, d.S, d.M, ilog2_exact(d.P), pro);

@@ -150,6 +150,12 @@ template <> struct FastCfg<__nv_bfloat16> {
 #ifndef MSDA_FWD_BATCH
 #define MSDA_FWD_BATCH 2
 #endif
+#ifndef MSDA_QMAP_FWD
+#define MSDA_QMAP_FWD 0   // 1: the warps of a CTA take CONSECUTIVE QUERIES of one head group (8 queries x 1 group) instead of
+#endif                    //    consecutive items (4 queries x 2 groups): neighbouring queries share corner rows in the SM's L1
+#ifndef MSDA_QMAP_BWD
+#define MSDA_QMAP_BWD 0
+#endif
 #ifndef MSDA_MERGE
 #define MSDA_MERGE 1   // 1: backward: corners of the points of one (query, head, level) that fall on the same pixel are
                        // merged by the lanes that own the points before anything is broadcast (TCE geometry only)
@@ -554,6 +560,26 @@ __device__ __forceinline__ void prologue_points(float (&xy)[2 * PPL], float (&a)
     }
 }
 
+// item -> (query, head group of the warp).  QMAP = false: item = nq * groups + hg.  QMAP = true: the items are taken in
+// super-blocks of (warps per CTA) queries x groups, and inside a super-block the head group is the slow index, so that the
+// warps of one CTA work on consecutive queries of the same heads.  Returns false for the padding of the last super-block.
+template <bool QMAP>
+__device__ __forceinline__ bool map_item(int64_t item, int64_t n_items, int groups, int64_t &nq, int &hg)
+{
+    if (!QMAP) {
+        nq = item / groups;
+        hg = static_cast<int>(item - nq * groups);
+        return item < n_items;
+    }
+    const int wpb = static_cast<int>(blockDim.x >> 5);
+    const int per = wpb * groups;
+    const int64_t super = item / per;
+    const int r = static_cast<int>(item - super * per);
+    hg = r / wpb;
+    nq = super * wpb + (r - hg * wpb);
+    return nq < n_items / groups;
+}
+
 // --------------------------------------------------------------------------------------------
 // FAST forward.  One warp = HPW heads of one (frame, query).
 //   item = nq * (M / HPW) + head_group
@@ -572,12 +598,11 @@ fwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 
     const int lane = threadIdx.x & 31;
     const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (item >= n_items) return;   // warp-uniform
-
     if (TCE) { M = 8; log2P = 2; }
     const int groups = M / HPW;
-    const int64_t nq = item / groups;
-    const int hg = static_cast<int>(item - nq * groups);
+    int64_t nq;
+    int hg;
+    if (!map_item<MSDA_QMAP_FWD != 0>(item, n_items, groups, nq, hg)) return;   // warp-uniform
     const int64_t n = nq / Lq;
     const int g = lane / LPH, j = lane % LPH;
     const int m = hg * HPW + g;
@@ -749,12 +774,11 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 
     const int lane = threadIdx.x & 31;
     const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (item >= n_items) return;
-
     if (TCE) { M = 8; log2P = 2; }
     const int groups = M / HPW;
-    const int64_t nq = item / groups;
-    const int hg = static_cast<int>(item - nq * groups);
+    int64_t nq;
+    int hg;
+    if (!map_item<MSDA_QMAP_BWD != 0>(item, n_items, groups, nq, hg)) return;
     const int64_t n = nq / Lq;
     const int g = lane / LPH, j = lane % LPH;
     const int m = hg * HPW + g;
