@@ -215,13 +215,6 @@ int launch_bwd_fast(const Dims &d, const void *value, const int64_t *shapes, con
     if (items == 0) return MSDA_OK;
     constexpr int threads = 256;
     auto kern = (d.M == 8 && d.P == 4) ? msda::bwd_fast_kernel<VT, LT, GT, PRO, true> : msda::bwd_fast_kernel<VT, LT, GT, PRO, false>;
-#if MSDA_PAIR
-    // two consecutive queries x two heads per warp (cross-query merging of the reductions): same number of warps, needs
-    // both queries of a pair in one frame (even Lq), the 8-lanes-per-head layout and no fused prologue
-    if constexpr (!PRO && msda::BwdLanes<VT, GT>::LPH == 8) {
-        if (d.M == 8 && d.P == 4 && d.Lq % 2 == 0) kern = msda::bwd_fast_kernel<VT, LT, GT, false, true, true>;
-    }
-#endif
     kern<<<grid_for_items(d.N * d.Lq, d.M / HPW, threads, MSDA_QMAP_BWD != 0), threads, 0, st>>>(
         static_cast<const VT *>(value), shapes, lsi, static_cast<const LT *>(loc),
         static_cast<const LT *>(aw), static_cast<const VT *>(go), gv, static_cast<LT *>(gl),

@@ -156,9 +156,6 @@ template <> struct FastCfg<__nv_bfloat16> {
 #ifndef MSDA_QMAP_BWD
 #define MSDA_QMAP_BWD 0
 #endif
-#ifndef MSDA_PAIR
-#define MSDA_PAIR 0    // 1: backward, fp32 accumulation, TCE geometry, even Lq: a warp takes 2 consecutive queries x 2 heads
-#endif                 //    and also merges the corners the two queries share (one reduction carries both contributions)
 #ifndef MSDA_MERGE
 #define MSDA_MERGE 1   // 1: backward: corners of the points of one (query, head, level) that fall on the same pixel are
                        // merged by the lanes that own the points before anything is broadcast (TCE geometry only)
@@ -737,24 +734,10 @@ __device__ __forceinline__ void red_add_v4_bf16x2_if(int pred, void *addr, uint3
 // 64-byte requests and the L2 sustained 20 % fewer line updates) or directly in 16 bits
 // (GT = VT, 4 lanes x 8 channels, one 64-byte bf16x2 request per line).
 template <typename VT, typename GT, int CPL> struct GradScatter;
-// add2: one reduction that carries the contributions of TWO queries to the same pixel (w * go + wo * go2); the second
-// term is skipped when wo == 0 so that a non-finite grad_out of the other query cannot leak into rows it does not touch
-__device__ __forceinline__ void red_two_queries(int pred, char *p, float w, const float (&go)[4], float wo, const float (&go2)[4])
-{
-    float v0 = w * go[0], v1 = w * go[1], v2 = w * go[2], v3 = w * go[3];
-    if (wo != 0.f) {
-        v0 = fmaf(wo, go2[0], v0); v1 = fmaf(wo, go2[1], v1); v2 = fmaf(wo, go2[2], v2); v3 = fmaf(wo, go2[3], v3);
-    }
-    red_add_v4_f32_if(pred, p, v0, v1, v2, v3);
-}
 template <> struct GradScatter<float, float, 4> {
     static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[4])
     {
         red_add_v4_f32_if(pred, p, w * go[0], w * go[1], w * go[2], w * go[3]);
-    }
-    static __device__ __forceinline__ void add2(int pred, char *p, float w, const float (&go)[4], float wo, const float (&go2)[4])
-    {
-        red_two_queries(pred, p, w, go, wo, go2);
     }
 };
 template <> struct GradScatter<__nv_bfloat16, float, 4> {
@@ -762,20 +745,12 @@ template <> struct GradScatter<__nv_bfloat16, float, 4> {
     {
         red_add_v4_f32_if(pred, p, w * go[0], w * go[1], w * go[2], w * go[3]);
     }
-    static __device__ __forceinline__ void add2(int pred, char *p, float w, const float (&go)[4], float wo, const float (&go2)[4])
-    {
-        red_two_queries(pred, p, w, go, wo, go2);
-    }
 };
 template <> struct GradScatter<__nv_bfloat16, __nv_bfloat16, 8> {
     static __device__ __forceinline__ void add(int pred, char *p, float w, const float (&go)[8])
     {
         red_add_v4_bf16x2_if(pred, p, pack_bf16x2(w * go[0], w * go[1]), pack_bf16x2(w * go[2], w * go[3]),
                              pack_bf16x2(w * go[4], w * go[5]), pack_bf16x2(w * go[6], w * go[7]));
-    }
-    static __device__ __forceinline__ void add2(int pred, char *p, float w, const float (&go)[8], float, const float (&)[8])
-    {
-        add(pred, p, w, go);      // the two-query warp layout exists for the 8-lanes-per-head kernels only
     }
 };
 
@@ -786,12 +761,7 @@ template <> struct BwdLanes<__nv_bfloat16, float> { static constexpr int LPH = 8
 // --------------------------------------------------------------------------------------------
 // FAST backward.
 // --------------------------------------------------------------------------------------------
-// PAIR = true (TCE geometry, 8 lanes per head, no prologue, even Lq): the four lane groups of a warp are
-// (query A, head h), (A, h+1), (B, h), (B, h+1) with B = A + 1, instead of four heads of one query.  Consecutive queries
-// sample overlapping pixels, so after the merge inside each (query, head, level) the lanes of query B fold the corners
-// they share with the same lanes' points of query A into a second weight per corner of A, and A's reduction carries
-// w_A * go_A + w_B * go_B (grad_out rows exchanged once per warp with shfl.xor 16).
-template <typename VT, typename LT, typename GT, bool PROLOGUE, bool TCE, bool PAIR = false>
+template <typename VT, typename LT, typename GT, bool PROLOGUE, bool TCE>
 __global__ void __launch_bounds__(256, (BwdLanes<VT, GT>::LPH == 8 ? MSDA_BWD_MIN_BLOCKS_F32 : MSDA_BWD_MIN_BLOCKS_BF16))
 bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes,
                 const int64_t *__restrict__ lsi, const LT *__restrict__ loc,
@@ -809,24 +779,17 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
     int64_t nq;
     int hg;
     if (!map_item<MSDA_QMAP_BWD != 0>(item, n_items, groups, nq, hg)) return;
-    const int g = lane / LPH, j = lane % LPH;
-    int m = hg * HPW + g;
-    if constexpr (PAIR) {
-        static_assert(LPH == 8 && !PROLOGUE && TCE, "two-query warps: fp32 accumulation, TCE geometry, no prologue");
-        const int64_t qp = item / (M / 2);                       // item = query pair * (M / 2) + head pair
-        const int hp = static_cast<int>(item - qp * (M / 2));
-        nq = 2 * qp + (g >> 1);                                  // per lane group from here on
-        m = 2 * hp + (g & 1);
-    }
     const int64_t n = nq / Lq;
-    const int64_t qh = nq * M + m;                               // this lane group's (query, head)
+    const int g = lane / LPH, j = lane % LPH;
+    const int m = hg * HPW + g;
 
+    const int64_t qh0 = nq * M + hg * HPW;
     float xy[2 * PPL], a[PPL];
-    PointIO<LT, PPL>::load_loc(loc + qh * (kFastLP * 2) + j * (2 * PPL), xy);
-    PointIO<LT, PPL>::load_aw(aw + qh * kFastLP + j * PPL, a);
+    PointIO<LT, PPL>::load_loc(loc + qh0 * (kFastLP * 2) + lane * (2 * PPL), xy);
+    PointIO<LT, PPL>::load_aw(aw + qh0 * kFastLP + lane * PPL, a);
 
     float go[CPL];
-    IO::load_stream(grad_out + qh * kFastD + j * CPL, go);
+    IO::load_stream(grad_out + (nq * M + m) * kFastD + j * CPL, go);
 
     int Hs[PPL], Ws[PPL], starts[PPL], lv[PPL];
 #pragma unroll
@@ -846,32 +809,6 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
 #if MSDA_MERGE
     if (TCE) merge_level<PPL, LPH>(mp, Ws[0], j);
 #endif
-    // PAIR: what query B adds to the corners of query A (same head, same lane: the same two point slots of the level)
-    float woth[PPL][4];
-    float go2[CPL];
-#pragma unroll
-    for (int pp = 0; pp < PPL; ++pp) woth[pp][0] = woth[pp][1] = woth[pp][2] = woth[pp][3] = 0.f;
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) go2[c] = 0.f;
-    if constexpr (PAIR) {
-        const bool second = (g >> 1) != 0;
-        const int pa0 = __shfl_xor_sync(kFull, mp[0].packed, 16);
-        const int pa1 = __shfl_xor_sync(kFull, mp[1].packed, 16);
-        float add0[4] = {0.f, 0.f, 0.f, 0.f}, add1[4] = {0.f, 0.f, 0.f, 0.f};
-        fold_into(add0, pa0 & 15, pa0 >> 8, mp[0], Ws[0], second);
-        fold_into(add1, pa1 & 15, pa1 >> 8, mp[0], Ws[0], second);
-        fold_into(add0, pa0 & 15, pa0 >> 8, mp[1], Ws[0], second);
-        fold_into(add1, pa1 & 15, pa1 >> 8, mp[1], Ws[0], second);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float r0 = __shfl_xor_sync(kFull, add0[k], 16);
-            const float r1 = __shfl_xor_sync(kFull, add1[k], 16);
-            woth[0][k] = second ? 0.f : r0;
-            woth[1][k] = second ? 0.f : r1;
-        }
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) go2[c] = __shfl_xor_sync(kFull, go[c], 16);
-    }
 
     const int pix = M * kFastD;
     const int pixb = pix * static_cast<int>(sizeof(VT));
@@ -925,20 +862,10 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
         }
         if (kReds) {
             // ... but a pixel shared with an earlier point of the level is reduced once, with the summed weight
-            if constexpr (PAIR) {
-                float wo[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) wo[k] = __shfl_sync(kFull, woth[pp][k], src, LPH);
-                GradScatter<VT, GT, CPL>::add2(pv.amask() & 1, g0, pv.w[0], go, wo[0], go2);
-                GradScatter<VT, GT, CPL>::add2(pv.amask() & 2, g0 + gpixb, pv.w[1], go, wo[1], go2);
-                GradScatter<VT, GT, CPL>::add2(pv.amask() & 4, g1, pv.w[2], go, wo[2], go2);
-                GradScatter<VT, GT, CPL>::add2(pv.amask() & 8, g1 + gpixb, pv.w[3], go, wo[3], go2);
-            } else {
-                GradScatter<VT, GT, CPL>::add(pv.amask() & 1, g0, pv.w[0], go);
-                GradScatter<VT, GT, CPL>::add(pv.amask() & 2, g0 + gpixb, pv.w[1], go);
-                GradScatter<VT, GT, CPL>::add(pv.amask() & 4, g1, pv.w[2], go);
-                GradScatter<VT, GT, CPL>::add(pv.amask() & 8, g1 + gpixb, pv.w[3], go);
-            }
+            GradScatter<VT, GT, CPL>::add(pv.amask() & 1, g0, pv.w[0], go);
+            GradScatter<VT, GT, CPL>::add(pv.amask() & 2, g0 + gpixb, pv.w[1], go);
+            GradScatter<VT, GT, CPL>::add(pv.amask() & 4, g1, pv.w[2], go);
+            GradScatter<VT, GT, CPL>::add(pv.amask() & 8, g1 + gpixb, pv.w[3], go);
         }
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
@@ -1000,8 +927,8 @@ bwd_fast_kernel(const VT *__restrict__ value, const int64_t *__restrict__ shapes
             }
         }
     }
-    PointIO<LT, PPL>::store_loc(grad_loc + qh * (kFastLP * 2) + j * (2 * PPL), gxy);
-    PointIO<LT, PPL>::store_aw(grad_aw + qh * kFastLP + j * PPL, ga);
+    PointIO<LT, PPL>::store_loc(grad_loc + qh0 * (kFastLP * 2) + lane * (2 * PPL), gxy);
+    PointIO<LT, PPL>::store_aw(grad_aw + qh0 * kFastLP + lane * PPL, ga);
 }
 
 // --------------------------------------------------------------------------------------------
